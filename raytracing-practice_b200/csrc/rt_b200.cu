@@ -1,0 +1,928 @@
+// rt_b200.cu — kernels + the C-ABI of include/rt_b200.h (librt_b200.so), sm_100a only.
+//
+// The hot path — camera::render's pixel x sample loop with its recursive ray_color
+// (src/core/camera.hpp:29-72, 180-232) — is ONE persistent megakernel:
+//   * grid = #SMs CTAs (one per SM), each staging the top of the BVH in shared memory;
+//   * work item = (pixel, chunk of consecutive sample indices); lanes pull items from a global
+//     atomic counter and REGENERATE a camera path the moment theirs ends, so a warp never
+//     idles on its longest path: every loop iteration is "trace one segment + shade" for all
+//     32 lanes (the recursion of ray_color is a pure tail product);
+//   * every sample is quantised to 2^-32 fixed point and summed as int64: integer addition is
+//     associative, so the image is bit-identical for any split of samples over lanes, CTAs,
+//     launches and GPUs (the multi-GPU reduce is an exact ncclInt64 sum or peer red.add.u64).
+// There is no CPU fallback: rt_init fails without a device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "device_scene.h"
+#include "rt_device.cuh"
+#include "scene_build.hpp"
+
+namespace rtb200 {
+
+struct CameraDev {
+  float3 center, p00c, du, dv, ddu, ddv, bg;
+  int W, H, max_depth, defocus;
+};
+
+struct RenderParams {
+  DeviceScene sc;
+  CameraDev cam;
+  uint2 key;
+  int sample_begin, sample_count, chunk, n_chunks;
+  int tiles_x, tiles_y;
+  unsigned long long n_items;
+  unsigned long long* accum;     // 3 x int64 per pixel (two's complement adds)
+  unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
+  int smem_nodes;
+};
+
+constexpr int kRenderThreads = 512;
+constexpr float kFixScale = 4294967296.0f;  // 2^32
+
+__device__ __forceinline__ long long to_fixed(float v) {
+  // NaN -> 0 (a NaN sample would poison the pixel); clamp keeps 2^31 samples from overflowing
+  v = (v == v) ? fminf(fmaxf(v, 0.0f), 1.0e6f) : 0.0f;
+  return __float2ll_rn(v * kFixScale);
+}
+
+__global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
+  extern __shared__ float4 s_nodes[];
+  for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
+  __syncthreads();
+  const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
+  const DeviceScene& sc = P.sc;
+  const float INF = __int_as_float(0x7f800000);
+  const unsigned long long per_chunk = (unsigned long long)P.tiles_x * P.tiles_y * 32ull;
+
+  unsigned long long item = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long acc_r = 0, acc_g = 0, acc_b = 0;
+  int pixel = -1, px = 0, py = 0, s = 0, s_end = 0;
+  bool alive = false;
+  unsigned int n_rays = 0, n_samples = 0;
+  PathKey key{P.key, 0u, 0u};
+  float3 o = f3(0, 0, 0), d = f3(0, 0, 1), beta = f3(1, 1, 1), L = f3(0, 0, 0);
+  float time = 0.0f;
+  int depth = 0;
+  uint32_t bounce = 1, skip = REF_NONE;
+
+  for (;;) {
+    if (!alive) {
+      if (s == s_end) {
+        if (pixel >= 0) {  // flush the finished item
+          unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
+          if (acc_r) atomicAdd(dst + 0, (unsigned long long)acc_r);
+          if (acc_g) atomicAdd(dst + 1, (unsigned long long)acc_g);
+          if (acc_b) atomicAdd(dst + 2, (unsigned long long)acc_b);
+          acc_r = acc_g = acc_b = 0;
+          pixel = -1;
+        }
+        bool got = false;
+        while (item < P.n_items) {
+          unsigned long long chunk = item / per_chunk, q = item % per_chunk;
+          unsigned int tile = (unsigned int)(q >> 5), lane = (unsigned int)(q & 31u);
+          px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
+          py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
+          item = atomicAdd(P.counters, 1ull);  // my next candidate
+          if (px < P.cam.W && py < P.cam.H) {
+            pixel = py * P.cam.W + px;
+            s = P.sample_begin + int(chunk) * P.chunk;
+            s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
+            got = s < s_end;
+            if (got) break;
+            pixel = -1;
+          }
+        }
+        if (!got) break;
+        key.pixel = uint32_t(pixel);
+      }
+      // ---- camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time ----
+      key.sample = uint32_t(s++);
+      n_samples++;
+      uint4 r0 = rng_block(key, 0u, 0u);
+      float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
+      time = u01(r0.z);
+      float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
+      o = P.cam.center;
+      if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
+        uint4 r1 = rng_block(key, 0u, 1u);
+        float rr = sqrtf(u01(r1.x)), sn, cs;
+        sincospif(2.0f * u01(r1.y), &sn, &cs);
+        float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
+        o = o + off;
+        dir = dir - off;
+      }
+      d = dir;
+      beta = f3(1.0f, 1.0f, 1.0f);
+      L = f3(0.0f, 0.0f, 0.0f);
+      depth = P.cam.max_depth;
+      bounce = 1;
+      skip = REF_NONE;
+      alive = depth > 0;
+      if (!alive) continue;
+    }
+    // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
+    n_rays++;
+    uint4 rnd = rng_block(key, bounce, 0u);
+    MediumRng mr{&key, bounce, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
+    Hit h = closest_hit(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr);
+    if (h.ref == REF_NONE) {
+      L = L + beta * P.cam.bg;
+      alive = false;
+    } else {
+      Surface sf = surface_at(sc, h, o, d, time);
+      float3 emit, atten, d_out;
+      bool cont = scatter_ray(sc, sf, d, rnd, emit, atten, d_out);
+      L = L + beta * emit;
+      if (cont) {
+        beta = beta * atten;
+        o = sf.p;
+        d = d_out;
+        skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
+        bounce++;
+        alive = --depth > 0;
+      } else {
+        alive = false;
+      }
+    }
+    if (!alive) {
+      acc_r += to_fixed(L.x);
+      acc_g += to_fixed(L.y);
+      acc_b += to_fixed(L.z);
+    }
+  }
+  // ---- counters: warp-reduce, one atomic per warp ---------------------------------------
+  unsigned int rays = n_rays, smp = n_samples;
+  for (int off = 16; off > 0; off >>= 1) {
+    rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
+    smp += __shfl_down_sync(0xFFFFFFFFu, smp, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(P.counters + 1, (unsigned long long)rays);
+    atomicAdd(P.counters + 2, (unsigned long long)smp);
+  }
+}
+
+// ---- write_color (common/color.hpp:26-58) on the device, in double like the reference ----
+__global__ void finalize_kernel(const long long* __restrict__ accum, long long n_values, double scale, float* __restrict__ radiance,
+                                unsigned char* __restrict__ rgb8) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_values) return;
+  double lin = double(accum[i]) * (1.0 / 4294967296.0) * scale;
+  if (radiance) radiance[i] = float(lin);
+  if (rgb8) {
+    double g = lin > 0.0 ? sqrt(lin) : 0.0;
+    const double hi = double(0.999f);
+    g = g < 0.0 ? 0.0 : (g > hi ? hi : g);
+    rgb8[i] = (unsigned char)(int(256 * g));
+  }
+}
+
+// ---- closest-hit queries for the parity harness ---------------------------------------------
+struct TraceParams {
+  DeviceScene sc;
+  long long n;
+  const double* origin;
+  const double* direction;
+  const double* time;
+  double tmin, tmax;
+  int flags;
+  unsigned long long seed;
+  int* prim_id;
+  double* t;
+  double* normal;
+  unsigned char* front;
+  int smem_nodes;
+};
+
+// fp32 conservative traversal; EVERY candidate primitive is evaluated by the fp64 routines that
+// follow sphere::hit / quad::hit operation for operation, and the winner is chosen by the
+// reference's visit order on exact ties (hittable_list.hpp:47-61).
+__device__ void exact_closest(const DeviceScene& sc, const NodeSource& ns, const XRay& r, double tmin, double tmax, int& out_pid, XRec& out_rec) {
+  float3 o = f3(float(r.o.x.v), float(r.o.y.v), float(r.o.z.v)), d = f3(float(r.d.x.v), float(r.d.y.v), float(r.d.z.v));
+  float3 inv = f3(fabsf(d.x) > 1e-30f ? 1.0f / d.x : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? 1.0f / d.y : copysignf(1e30f, d.y),
+                  fabsf(d.z) > 1e-30f ? 1.0f / d.z : copysignf(1e30f, d.z));
+  float3 ood = o * inv;
+  const float eps = 4e-6f * (sc.scene_abs_max + fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+  const float tminf = float(tmin) - fabsf(float(tmin)) * 1e-5f - 1e-30f;
+  double best_t = tmax;
+  int best_order = -1, best_is_quad = 0;
+  out_pid = -1;
+  int stack[kStackDepth];
+  int sp = 0, cur = 0;
+  for (;;) {
+    if (cur >= 0) {
+      float4 a, b, c;
+      int c0, c1;
+      load_node(ns, cur, a, b, c, c0, c1);
+      float bestf = best_t < 3e38 ? float(best_t) * (1.0f + 1e-5f) + 1e-30f : __int_as_float(0x7f800000);
+      float x0 = fmaf(a.x - eps, inv.x, -ood.x), x1 = fmaf(a.w + eps, inv.x, -ood.x);
+      float y0 = fmaf(a.y - eps, inv.y, -ood.y), y1 = fmaf(b.x + eps, inv.y, -ood.y);
+      float z0 = fmaf(a.z - eps, inv.z, -ood.z), z1 = fmaf(b.y + eps, inv.z, -ood.z);
+      float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tminf));
+      float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestf));
+      x0 = fmaf(b.z - eps, inv.x, -ood.x), x1 = fmaf(c.y + eps, inv.x, -ood.x);
+      y0 = fmaf(b.w - eps, inv.y, -ood.y), y1 = fmaf(c.z + eps, inv.y, -ood.y);
+      z0 = fmaf(c.x - eps, inv.z, -ood.z), z1 = fmaf(c.w + eps, inv.z, -ood.z);
+      float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tminf));
+      float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestf));
+      // an empty child has lo=+inf, hi=-inf: lo-eps = +inf, hi+eps = -inf, still never entered
+      bool h0 = n0 <= f0 * (1.0f + 1e-5f) + 1e-30f, h1 = n1 <= f1 * (1.0f + 1e-5f) + 1e-30f;
+      if (h0 && h1) {
+        if (sp < kStackDepth) stack[sp++] = c1;
+        cur = c0;
+        continue;
+      }
+      if (h0) { cur = c0; continue; }
+      if (h1) { cur = c1; continue; }
+    } else {
+      int code = ~cur;
+      int first = code >> 3, count = (code & 7) + 1;
+      for (int k = 0; k < count; k++) {
+        uint32_t ref = sc.leaf_refs[first + k];
+        uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        if (ref == REF_NONE || type == REF_MEDIUM) continue;  // media are transparent here
+        XRec rec;
+        int order, pid, is_quad = type == REF_QUAD;
+        bool ok;
+        if (is_quad) {
+          const XQuad& q = sc.xquads[idx];
+          ok = exact_quad(sc, q, r, tmin, tmax, rec);
+          order = q.order, pid = q.pid;
+        } else {
+          const XSphere& q = sc.xspheres[idx];
+          ok = exact_sphere(sc, q, r, tmin, tmax, rec);
+          order = q.order, pid = q.pid;
+        }
+        if (!ok) continue;
+        bool take;
+        if (best_order < 0) {
+          take = is_quad ? rec.t.v <= best_t : rec.t.v < best_t;
+        } else if (rec.t.v != best_t) {
+          take = rec.t.v < best_t;
+        } else {  // exact tie: the later visit wins iff it is a quad (contains vs surrounds)
+          take = order > best_order ? is_quad != 0 : best_is_quad == 0;
+        }
+        if (take) best_t = rec.t.v, best_order = order, best_is_quad = is_quad, out_pid = pid, out_rec = rec;
+      }
+    }
+    if (sp == 0) return;
+    cur = stack[--sp];
+  }
+}
+
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
+  extern __shared__ float4 s_nodes[];
+  for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
+  __syncthreads();
+  const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const DeviceScene& sc = P.sc;
+  double tm = P.time ? P.time[i] : 0.0;
+  int pid = -1;
+  double t = INFINITY, nx = 0, ny = 0, nz = 0;
+  bool front = false;
+  if (P.flags & RT_TRACE_EXACT) {
+    XRay r{SV(P.origin + 3 * i), SV(P.direction + 3 * i), S(tm)};
+    XRec rec;
+    exact_closest(sc, ns, r, P.tmin, P.tmax, pid, rec);
+    if (pid >= 0) t = rec.t.v, nx = rec.n.x.v, ny = rec.n.y.v, nz = rec.n.z.v, front = rec.front;
+  } else {
+    float3 o = f3(float(P.origin[3 * i]), float(P.origin[3 * i + 1]), float(P.origin[3 * i + 2]));
+    float3 d = f3(float(P.direction[3 * i]), float(P.direction[3 * i + 1]), float(P.direction[3 * i + 2]));
+    PathKey key{make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32)), (uint32_t)i, 0u};
+    MediumRng mr{&key, 1u, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
+    bool media = sc.n_media && !(P.flags & RT_TRACE_SKIP_MEDIA);
+    float tmaxf = P.tmax < 3e38 ? float(P.tmax) : __int_as_float(0x7f800000);
+    Hit h = closest_hit(sc, ns, o, d, float(tm), float(P.tmin), tmaxf, REF_NONE, media ? &mr : nullptr);
+    if (h.ref != REF_NONE) {
+      Surface sf = surface_at(sc, h, o, d, float(tm));
+      uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
+      pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
+      t = h.t, nx = sf.n.x, ny = sf.n.y, nz = sf.n.z, front = sf.front;
+    }
+  }
+  if (P.prim_id) P.prim_id[i] = pid;
+  if (P.t) P.t[i] = t;
+  if (P.normal) P.normal[3 * i] = nx, P.normal[3 * i + 1] = ny, P.normal[3 * i + 2] = nz;
+  if (P.front) P.front[i] = front;
+}
+
+// pixel-centre rays in double with the operation order of camera::get_ray at zero jitter
+// (camera.hpp:147,156): pixel00 + (i * du) + (j * dv), direction = sample - center.
+__global__ void center_rays_kernel(rt_camera_frame f, double* origin, double* direction) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= f.image_width) return;
+  sv p00 = SV(f.pixel00_loc), du = SV(f.pixel_delta_u), dv = SV(f.pixel_delta_v), c = SV(f.center);
+  sv ps = p00 + (S(double(i) + 0.0) * du) + (S(double(j) + 0.0) * dv);
+  sv dir = ps - c;
+  long long p = ((long long)j * f.image_width + i) * 3;
+  origin[p] = c.x.v, origin[p + 1] = c.y.v, origin[p + 2] = c.z.v;
+  direction[p] = dir.x.v, direction[p + 1] = dir.y.v, direction[p + 2] = dir.z.v;
+}
+
+__global__ void medium_spans_kernel(DeviceScene sc, int medium, long long n, const double* origin, const double* direction, const double* time, double* t1,
+                                    double* t2) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float3 o = f3(float(origin[3 * i]), float(origin[3 * i + 1]), float(origin[3 * i + 2]));
+  float3 d = f3(float(direction[3 * i]), float(direction[3 * i + 1]), float(direction[3 * i + 2]));
+  float a = NAN, b = NAN;
+  const float INF = __int_as_float(0x7f800000);
+  const DMedium m = sc.media[medium];
+  float x1, x2;
+  bool both = medium_span(sc, m, o, d, time ? float(time[i]) : 0.0f, x1, x2);
+  if (x1 != INF) a = x1;
+  if (both) b = x2;
+  t1[i] = a, t2[i] = b;
+}
+
+__global__ void eval_texture_kernel(DeviceScene sc, int tex, long long n, const double* uvp, float* rgb) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* q = uvp + 5 * i;
+  float3 c = texture_value(sc, tex, float(q[0]), float(q[1]), f3(float(q[2]), float(q[3]), float(q[4])));
+  rgb[3 * i] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
+}
+
+__global__ void eval_scatter_kernel(DeviceScene sc, int material, long long n, unsigned long long seed, const double* dir_in, const double* normal,
+                                    const unsigned char* front, float* dir_out, float* atten, unsigned char* scattered) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Surface s;
+  s.p = f3(0, 0, 0);
+  s.n = f3(float(normal[3 * i]), float(normal[3 * i + 1]), float(normal[3 * i + 2]));
+  s.u = s.v = 0.0f;
+  s.front = front[i] != 0;
+  s.material = material;
+  PathKey key{make_uint2((unsigned)seed, (unsigned)(seed >> 32)), (uint32_t)i, (uint32_t)(i >> 32)};
+  uint4 rnd = rng_block(key, 1u, 0u);
+  float3 emit, a = f3(0, 0, 0), dout = f3(0, 0, 0);
+  bool ok = scatter_ray(sc, s, f3(float(dir_in[3 * i]), float(dir_in[3 * i + 1]), float(dir_in[3 * i + 2])), rnd, emit, a, dout);
+  scattered[i] = ok;
+  dir_out[3 * i] = dout.x, dir_out[3 * i + 1] = dout.y, dir_out[3 * i + 2] = dout.z;
+  atten[3 * i] = a.x, atten[3 * i + 1] = a.y, atten[3 * i + 2] = a.z;
+}
+
+}  // namespace rtb200
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+using namespace rtb200;
+
+namespace {
+std::mutex g_err_mutex;
+std::string g_init_error = "";
+
+template <typename T>
+struct DevArray {
+  T* ptr = nullptr;
+  size_t count = 0;
+};
+}  // namespace
+
+struct rt_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  std::string error;
+  std::vector<void*> scene_allocs;
+  DeviceScene sc;
+  bool has_scene = false;
+  HostScene host;
+  unsigned long long* accum = nullptr;
+  size_t accum_values = 0;
+  int acc_w = 0, acc_h = 0;
+  unsigned long long* counters = nullptr;  // 4 x u64
+  unsigned long long rays_total = 0, samples_total = 0;
+  int smem_nodes = 0;
+  int launches = 0;
+};
+
+#define RT_CUDA(ctx, call)                                                                          \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      (ctx)->error = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return RT_ERR_CUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+
+static int fail(rt_ctx* ctx, int code, const std::string& msg) {
+  ctx->error = msg;
+  return code;
+}
+
+template <typename T>
+static int upload(rt_ctx* ctx, const std::vector<T>& v, const T** out) {
+  *out = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  void* p = nullptr;
+  RT_CUDA(ctx, cudaMalloc(&p, bytes));
+  ctx->scene_allocs.push_back(p);
+  if (!v.empty()) RT_CUDA(ctx, cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = static_cast<const T*>(p);
+  return RT_OK;
+}
+
+static void free_scene(rt_ctx* ctx) {
+  for (void* p : ctx->scene_allocs) cudaFree(p);
+  ctx->scene_allocs.clear();
+  ctx->has_scene = false;
+}
+
+// ---- parity-harness entry points -----------------------------------------------------------
+namespace {
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  template <typename T>
+  T* to_device(const T* host, size_t n) {
+    if (!host) return nullptr;
+    T* p = alloc<T>(n);
+    if (p && cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return p;
+  }
+};
+
+int run_trace(rt_ctx* ctx, long long n, const double* d_origin, const double* d_dir, const double* d_time, double tmin, double tmax, int flags,
+              int32_t* prim_id, double* t, double* normal, uint8_t* front_face, Scratch& sx) {
+  TraceParams P;
+  std::memset(&P, 0, sizeof P);
+  P.sc = ctx->sc;
+  P.n = n;
+  P.origin = d_origin, P.direction = d_dir, P.time = d_time;
+  P.tmin = tmin, P.tmax = tmax, P.flags = flags, P.seed = 0;
+  P.prim_id = prim_id ? sx.alloc<int>(size_t(n)) : nullptr;
+  P.t = t ? sx.alloc<double>(size_t(n)) : nullptr;
+  P.normal = normal ? sx.alloc<double>(size_t(3 * n)) : nullptr;
+  P.front = front_face ? sx.alloc<unsigned char>(size_t(n)) : nullptr;
+  if ((prim_id && !P.prim_id) || (t && !P.t) || (normal && !P.normal) || (front_face && !P.front)) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+  P.smem_nodes = std::min(ctx->smem_nodes, int((ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 0) / 64));
+  size_t smem = size_t(P.smem_nodes) * 64;
+  RT_CUDA(ctx, cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (n > 0) {
+    trace_kernel<<<unsigned((n + 255) / 256), 256, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+  }
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (prim_id) RT_CUDA(ctx, cudaMemcpy(prim_id, P.prim_id, size_t(n) * 4, cudaMemcpyDeviceToHost));
+  if (t) RT_CUDA(ctx, cudaMemcpy(t, P.t, size_t(n) * 8, cudaMemcpyDeviceToHost));
+  if (normal) RT_CUDA(ctx, cudaMemcpy(normal, P.normal, size_t(n) * 24, cudaMemcpyDeviceToHost));
+  if (front_face) RT_CUDA(ctx, cudaMemcpy(front_face, P.front, size_t(n), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rt_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return int(sizeof(rt_hittable));
+    case 1: return int(sizeof(rt_material));
+    case 2: return int(sizeof(rt_texture));
+    case 3: return int(sizeof(rt_image));
+    case 4: return int(sizeof(rt_perlin));
+    case 5: return int(sizeof(rt_scene_desc));
+    case 6: return int(sizeof(rt_camera_desc));
+    case 7: return int(sizeof(rt_camera_frame));
+    case 8: return int(sizeof(rt_render_opts));
+    case 9: return int(sizeof(rt_stats));
+  }
+  return -1;
+}
+
+// camera::initialize (src/core/camera.hpp:76-136), double, same operation order.
+int rt_camera_initialize(const rt_camera_desc* c, rt_camera_frame* f) {
+  if (!c || !f) return RT_ERR_INVALID;
+  using namespace build_detail;
+  const double pi = 3.1415926535897932385;
+  int W = c->image_width;
+  int H = static_cast<int>(c->image_width / c->aspect_ratio);
+  H = H < 1 ? 1 : H;
+  f->image_width = W;
+  f->image_height = H;
+  f->pixel_samples_scale = 1.0f / c->samples_per_pixel;  // float / int -> float (:83)
+  double theta = c->vfov * pi / 180.0f;
+  double h = std::tan(theta / 2);
+  double vh = 2 * h * c->focus_dist;
+  double vw = vh * (static_cast<double>(W) / H);
+  d3 from = ld(c->lookfrom), at = ld(c->lookat), vup = ld(c->vup);
+  auto unit = [](d3 v) { return (1 / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z)) * v; };
+  d3 w = unit(from - at);
+  d3 u = unit(cross(vup, w));
+  d3 v = cross(w, u);
+  d3 vu = vw * u;
+  d3 vv = vh * d3{-v.x, -v.y, -v.z};
+  d3 du = (1 / double(W)) * vu;
+  d3 dv = (1 / double(H)) * vv;
+  d3 ul = from - (c->focus_dist * w) - (1 / 2.0) * vu - (1 / 2.0) * vv;
+  d3 p00 = ul + 0.5 * (du + dv);
+  double dr = c->focus_dist * std::tan((c->defocus_angle * pi / 180.0f) / 2.0f);
+  d3 ddu = dr * u, ddv = dr * v;
+  const d3* src[9] = {&from, &p00, &du, &dv, &u, &v, &w, &ddu, &ddv};
+  double* dst[9] = {f->center, f->pixel00_loc, f->pixel_delta_u, f->pixel_delta_v, f->u, f->v, f->w, f->defocus_disk_u, f->defocus_disk_v};
+  for (int i = 0; i < 9; i++) dst[i][0] = src[i]->x, dst[i][1] = src[i]->y, dst[i][2] = src[i]->z;
+  return RT_OK;
+}
+
+int rt_init(int device, rt_ctx** out) {
+  if (!out) return RT_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_init_error = e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)
+                                    : "no such CUDA device " + std::to_string(device) + " (" + std::to_string(n) + " visible); there is no CPU fallback";
+    return RT_ERR_NO_DEVICE;
+  }
+  rt_ctx* ctx = new rt_ctx;
+  ctx->device = device;
+  std::memset(&ctx->sc, 0, sizeof ctx->sc);
+  auto bail = [&](const char* what, cudaError_t err) {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_init_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return RT_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+  *out = ctx;
+  return RT_OK;
+}
+
+void rt_shutdown(rt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_scene(ctx);
+  cudaFree(ctx->accum);
+  cudaFree(ctx->counters);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rt_last_error(rt_ctx* ctx) {
+  if (ctx) return ctx->error.c_str();
+  std::lock_guard<std::mutex> g(g_err_mutex);
+  return g_init_error.c_str();
+}
+
+int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!scene) return fail(ctx, RT_ERR_INVALID, "null scene");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  free_scene(ctx);
+  ctx->host = HostScene();
+  if (!build_host_scene(scene, ctx->host)) {
+    bool unsupported = ctx->host.error.find("unknown") != std::string::npos || ctx->host.error.find("not supported") != std::string::npos;
+    return fail(ctx, unsupported ? RT_ERR_UNSUPPORTED : RT_ERR_INVALID, ctx->host.error);
+  }
+  const HostScene& h = ctx->host;
+  if (h.bvh_depth > kStackDepth) return fail(ctx, RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+  DeviceScene& s = ctx->sc;
+  int rc;
+#define UP(field, vec) \
+  if ((rc = upload(ctx, vec, &s.field)) != RT_OK) return rc;
+  UP(nodes, h.nodes)
+  UP(leaf_refs, h.leaf_refs)
+  UP(spheres, h.spheres)
+  UP(sph_meta, h.sph_meta)
+  UP(quads, h.quads)
+  UP(quad_mat, h.quad_mat)
+  UP(media, h.media)
+  UP(medium_brefs, h.medium_brefs)
+  UP(materials, h.materials)
+  UP(textures, h.textures)
+  UP(texels, h.texels)
+  UP(images, h.images)
+  UP(perlin_vec, h.perlin_vec)
+  UP(perlin_perm, h.perlin_perm)
+  UP(rotations, h.rotations)
+  UP(xspheres, h.xspheres)
+  UP(xquads, h.xquads)
+  UP(xops, h.xops)
+  UP(xchains, h.xchains)
+#undef UP
+  s.n_nodes = int(h.nodes.size() / 4);
+  s.n_spheres = int(h.spheres.size() / 2);
+  s.n_quads = int(h.quads.size() / 3);
+  s.n_media = int(h.media.size());
+  s.n_materials = int(h.materials.size() / 2);
+  s.n_textures = int(h.textures.size() / 2);
+  s.scene_abs_max = h.scene_abs_max;
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // top of the BVH in shared memory: as many breadth-first nodes as fit beside the static needs
+  size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 0;
+  ctx->smem_nodes = int(std::min<size_t>(size_t(s.n_nodes), budget / 64));
+  ctx->has_scene = true;
+  return RT_OK;
+}
+
+static void fill_camera(const rt_camera_desc* cam, const rt_camera_frame& f, CameraDev& c) {
+  auto v3 = [](const double* p) { return make_float3(float(p[0]), float(p[1]), float(p[2])); };
+  c.center = v3(f.center);
+  // direction base relative to the centre, subtracted in double: |p00 - center| ~ focus_dist,
+  // so fp32 keeps sub-pixel precision even when the camera sits at |x| ~ 1e3
+  c.p00c = make_float3(float(f.pixel00_loc[0] - f.center[0]), float(f.pixel00_loc[1] - f.center[1]), float(f.pixel00_loc[2] - f.center[2]));
+  c.du = v3(f.pixel_delta_u);
+  c.dv = v3(f.pixel_delta_v);
+  c.ddu = v3(f.defocus_disk_u);
+  c.ddv = v3(f.defocus_disk_v);
+  c.bg = v3(cam->background);
+  c.W = f.image_width;
+  c.H = f.image_height;
+  c.max_depth = cam->max_depth;
+  c.defocus = cam->defocus_angle > 0.0f ? 1 : 0;  // camera.hpp:155
+}
+
+static int ensure_accum(rt_ctx* ctx, int W, int H, bool clear) {
+  size_t values = size_t(W) * H * 3;
+  if (values != ctx->accum_values || ctx->acc_w != W) {
+    cudaFree(ctx->accum);
+    ctx->accum = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&ctx->accum, values * 8));
+    ctx->accum_values = values;
+    ctx->acc_w = W, ctx->acc_h = H;
+    clear = true;
+  }
+  if (clear) {
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, values * 8, ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    ctx->rays_total = ctx->samples_total = 0;
+  }
+  return RT_OK;
+}
+
+int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!cam || !opts) return fail(ctx, RT_ERR_INVALID, "null camera / options");
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_render before rt_upload_scene");
+  if (cam->image_width <= 0 || cam->samples_per_pixel <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  rt_camera_frame f;
+  rt_camera_initialize(cam, &f);
+  int rc = ensure_accum(ctx, f.image_width, f.image_height, opts->clear != 0);
+  if (rc != RT_OK) return rc;
+
+  RenderParams P;
+  std::memset(&P, 0, sizeof P);
+  P.sc = ctx->sc;
+  fill_camera(cam, f, P.cam);
+  P.key = make_uint2((unsigned)opts->seed, (unsigned)(opts->seed >> 32));
+  P.sample_begin = opts->sample_begin;
+  P.sample_count = opts->sample_count > 0 ? opts->sample_count : cam->samples_per_pixel - opts->sample_begin;
+  if (P.sample_begin < 0 || P.sample_count <= 0) return fail(ctx, RT_ERR_INVALID, "empty sample range");
+  P.tiles_x = (f.image_width + 7) / 8;
+  P.tiles_y = (f.image_height + 3) / 4;
+  const int grid = ctx->sm_count;
+  const long long threads = (long long)grid * kRenderThreads;
+  // samples per work item: enough items (>= 8 per thread) for the dynamic balance, at most 32
+  long long total = (long long)f.image_width * f.image_height * P.sample_count;
+  long long chunk = total / (threads * 8);
+  P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, 32, (long long)P.sample_count})));
+  P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
+  P.n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull * (unsigned long long)P.n_chunks;
+  P.accum = opts->peer_accum ? static_cast<unsigned long long*>(opts->peer_accum) : ctx->accum;
+  P.counters = ctx->counters;
+  P.smem_nodes = ctx->smem_nodes;
+  size_t smem = size_t(P.smem_nodes) * 64;
+  RT_CUDA(ctx, cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  // counters[0] = first item not pre-assigned to a thread
+  unsigned long long first = (unsigned long long)threads;
+  RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  render_kernel<<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  RT_CUDA(ctx, cudaGetLastError());
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  return RT_OK;
+}
+
+int rt_synchronize(rt_ctx* ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
+int rt_accum_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes) {
+  if (!ctx || !dev_ptr || !bytes) return RT_ERR_INVALID;
+  if (!ctx->accum) return fail(ctx, RT_ERR_INVALID, "no accumulator yet (call rt_render first)");
+  *dev_ptr = ctx->accum;
+  *bytes = ctx->accum_values * 8;
+  return RT_OK;
+}
+
+int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t bytes) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!dst) return fail(ctx, RT_ERR_INVALID, "null destination");
+  if (!ctx->accum) return fail(ctx, RT_ERR_INVALID, "nothing rendered yet");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = ctx->accum_values;
+  if (kind == RT_BUF_ACCUM_I64) {
+    if (bytes < n * 8) return fail(ctx, RT_ERR_INVALID, "destination too small");
+    RT_CUDA(ctx, cudaMemcpyAsync(dst, ctx->accum, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+  }
+  if (spp <= 0) return fail(ctx, RT_ERR_INVALID, "samples_per_pixel must be positive");
+  const bool f32 = kind == RT_BUF_RADIANCE_F32;
+  if (!f32 && kind != RT_BUF_RGB8) return fail(ctx, RT_ERR_INVALID, "unknown buffer kind");
+  const size_t need = f32 ? n * 4 : n;
+  if (bytes < need) return fail(ctx, RT_ERR_INVALID, "destination too small");
+  void* tmp = nullptr;
+  RT_CUDA(ctx, cudaMalloc(&tmp, need));
+  const double scale = double(1.0f / float(spp));  // pixel_samples_scale, camera.hpp:83
+  finalize_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(ctx->accum), (long long)n, scale,
+                                                                      f32 ? static_cast<float*>(tmp) : nullptr,
+                                                                      f32 ? nullptr : static_cast<unsigned char*>(tmp));
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, need, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_download: ") + cudaGetErrorString(e));
+  return RT_OK;
+}
+
+int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
+  if (!ctx || !out) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memset(out, 0, sizeof *out);
+  unsigned long long c[4] = {0, 0, 0, 0};
+  RT_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
+  out->rays = c[1];
+  out->samples = c[2];
+  if (ctx->timed) {
+    float ms = 0;
+    RT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    out->last_render_ms = ms;
+  }
+  out->image_width = ctx->acc_w;
+  out->image_height = ctx->acc_h;
+  out->n_nodes = ctx->sc.n_nodes;
+  out->n_spheres = ctx->sc.n_spheres;
+  out->n_quads = ctx->sc.n_quads;
+  out->n_media = ctx->sc.n_media;
+  out->bvh_nodes_in_smem = ctx->smem_nodes;
+  out->kernel_launches = ctx->launches;
+  return RT_OK;
+}
+
+int rt_trace_rays(rt_ctx* ctx, int64_t n, const double* origin, const double* direction, const double* time, double tmin, double tmax, int32_t flags,
+                  int32_t* prim_id, double* t, double* normal, uint8_t* front_face) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_trace_rays before rt_upload_scene");
+  if (n < 0 || (n > 0 && (!origin || !direction))) return fail(ctx, RT_ERR_INVALID, "bad ray arrays");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch sx;
+  const double* d_o = sx.to_device(origin, size_t(3 * n));
+  const double* d_d = sx.to_device(direction, size_t(3 * n));
+  const double* d_t = sx.to_device(time, size_t(n));
+  if (n > 0 && (!d_o || !d_d || (time && !d_t))) return fail(ctx, RT_ERR_CUDA, "cudaMalloc / copy of the rays failed");
+  return run_trace(ctx, n, d_o, d_d, d_t, tmin, tmax, flags, prim_id, t, normal, front_face, sx);
+}
+
+int rt_primary_visibility(rt_ctx* ctx, const rt_camera_desc* cam, int32_t flags, int32_t* prim_id, double* t, double* normal) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_primary_visibility before rt_upload_scene");
+  if (!cam || cam->image_width <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  rt_camera_frame f;
+  rt_camera_initialize(cam, &f);
+  const long long n = (long long)f.image_width * f.image_height;
+  Scratch sx;
+  double* d_o = sx.alloc<double>(size_t(3 * n));
+  double* d_d = sx.alloc<double>(size_t(3 * n));
+  if (!d_o || !d_d) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+  dim3 grid((f.image_width + 127) / 128, f.image_height);
+  center_rays_kernel<<<grid, 128, 0, ctx->stream>>>(f, d_o, d_d);
+  ctx->launches++;
+  RT_CUDA(ctx, cudaGetLastError());
+  return run_trace(ctx, n, d_o, d_d, nullptr, 0.001, INFINITY, flags, prim_id, t, normal, nullptr, sx);
+}
+
+int rt_medium_spans(rt_ctx* ctx, int32_t medium_index, int64_t n, const double* origin, const double* direction, const double* time, double* t1,
+                    double* t2) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_medium_spans before rt_upload_scene");
+  if (medium_index < 0 || medium_index >= ctx->sc.n_media) return fail(ctx, RT_ERR_INVALID, "medium index out of range");
+  if (n < 0 || !origin || !direction || !t1 || !t2) return fail(ctx, RT_ERR_INVALID, "bad arrays");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch sx;
+  const double* d_o = sx.to_device(origin, size_t(3 * n));
+  const double* d_d = sx.to_device(direction, size_t(3 * n));
+  const double* d_t = sx.to_device(time, size_t(n));
+  double* d_1 = sx.alloc<double>(size_t(n));
+  double* d_2 = sx.alloc<double>(size_t(n));
+  if (!d_o || !d_d || !d_1 || !d_2) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+  if (n > 0) {
+    medium_spans_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, medium_index, n, d_o, d_d, d_t, d_1, d_2);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+  }
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(ctx, cudaMemcpy(t1, d_1, size_t(n) * 8, cudaMemcpyDeviceToHost));
+  RT_CUDA(ctx, cudaMemcpy(t2, d_2, size_t(n) * 8, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int rt_eval_texture(rt_ctx* ctx, int32_t texture, int64_t n, const double* uvp, float* rgb) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_eval_texture before rt_upload_scene");
+  if (texture < 0 || texture >= ctx->sc.n_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
+  if (n < 0 || !uvp || !rgb) return fail(ctx, RT_ERR_INVALID, "bad arrays");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch sx;
+  const double* d_in = sx.to_device(uvp, size_t(5 * n));
+  float* d_out = sx.alloc<float>(size_t(3 * n));
+  if (!d_in || !d_out) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+  if (n > 0) {
+    eval_texture_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, texture, n, d_in, d_out);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+  }
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(ctx, cudaMemcpy(rgb, d_out, size_t(n) * 12, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int rt_eval_scatter(rt_ctx* ctx, int32_t material, int64_t n, uint64_t seed, const double* dir_in, const double* normal, const uint8_t* front_face,
+                    float* dir_out, float* attenuation, uint8_t* scattered) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_eval_scatter before rt_upload_scene");
+  if (material < 0 || material >= ctx->sc.n_materials) return fail(ctx, RT_ERR_INVALID, "material index out of range");
+  if (n < 0 || !dir_in || !normal || !front_face || !dir_out || !attenuation || !scattered) return fail(ctx, RT_ERR_INVALID, "bad arrays");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  Scratch sx;
+  const double* d_di = sx.to_device(dir_in, size_t(3 * n));
+  const double* d_n = sx.to_device(normal, size_t(3 * n));
+  const unsigned char* d_f = sx.to_device(front_face, size_t(n));
+  float* d_do = sx.alloc<float>(size_t(3 * n));
+  float* d_a = sx.alloc<float>(size_t(3 * n));
+  unsigned char* d_s = sx.alloc<unsigned char>(size_t(n));
+  if (!d_di || !d_n || !d_f || !d_do || !d_a || !d_s) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+  if (n > 0) {
+    eval_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, material, n, seed, d_di, d_n, d_f, d_do, d_a, d_s);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+  }
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(ctx, cudaMemcpy(dir_out, d_do, size_t(n) * 12, cudaMemcpyDeviceToHost));
+  RT_CUDA(ctx, cudaMemcpy(attenuation, d_a, size_t(n) * 12, cudaMemcpyDeviceToHost));
+  RT_CUDA(ctx, cudaMemcpy(scattered, d_s, size_t(n), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+// Host-only view of the scene converter, for CPU tests of the host logic (no GPU needed):
+// fills counts[0..7] = nodes, spheres, quads, media, leaf refs, bvh depth, chains, materials.
+int rt_debug_build_stats(const rt_scene_desc* scene, int32_t* counts, double* sah_cost) {
+  HostScene h;
+  if (!build_host_scene(scene, h)) return RT_ERR_INVALID;
+  if (counts) {
+    counts[0] = int(h.nodes.size() / 4), counts[1] = int(h.spheres.size() / 2), counts[2] = int(h.quads.size() / 3);
+    counts[3] = int(h.media.size()), counts[4] = int(h.leaf_refs.size()), counts[5] = h.bvh_depth;
+    counts[6] = int(h.xchains.size()), counts[7] = int(h.materials.size() / 2);
+  }
+  if (sah_cost) *sah_cost = h.sah_cost;
+  return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,583 @@
+// rt_device.cuh — device-side building blocks of the B200 path tracer (sm_100a).
+//
+// What each block replaces in the reference (file:line under src/):
+//   philox4x32 / Rng         std::rand via random_double           common/rtweekend.hpp:23-39
+//   closest_hit              hittable_list::hit + bvh_node::hit    hittable/hittable_list.hpp:40-64,
+//                            + aabb::hit                           accelerator/bvh_node.hpp:80-94, aabb.hpp:61-112
+//   hit_sphere / hit_quad    sphere::hit / quad::hit               hittable/sphere.hpp:47-93, quad.hpp:44-114
+//   medium_sample            constant_medium::hit                  SURVEY.md Appendix B.2
+//   texture_value            texture::value (4 kinds) + perlin     core/texture.hpp:34-151, core/perlin.hpp:95-255
+//   scatter_ray              material::scatter / emitted (5 kinds) core/material.hpp:29-236, SURVEY B.3
+//   exact_*                  the same hit() routines in fp64 with the reference's operation order
+//                            (no FMA contraction), used only by the parity harness.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+
+namespace rtb200 {
+
+// ---------------------------------------------------------------------------------------
+// small float3 algebra
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+__device__ __forceinline__ float3 normalize3(float3 a) { return rsqrtf(dot(a, a)) * a; }
+
+// ---------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011), counter-based: the sample set of a (pixel, sample,
+// bounce) is a pure function of the key, so images do not depend on how samples are sharded
+// over threads, launches or GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// 24-bit uniform in [0,1): same granularity as the reference's int/float random_double
+// (rtweekend.hpp:26) but never exactly 1.0.
+__device__ __forceinline__ float u01(uint32_t x) { return float(x >> 8) * 5.9604644775390625e-8f; }
+
+struct PathKey {
+  uint2 key;       // seed
+  uint32_t pixel;  // counter.x
+  uint32_t sample; // counter.y
+};
+__device__ __forceinline__ uint4 rng_block(const PathKey& k, uint32_t bounce, uint32_t stream) {
+  return philox4x32_10(make_uint4(k.pixel, k.sample, bounce, stream), k.key);
+}
+
+// uniform direction on the unit sphere from two uniforms: distribution-identical to the
+// reference's rejection sampler random_unit_vector (common/vec3.hpp:172-184).
+__device__ __forceinline__ float3 unit_vector_from(float u0, float u1) {
+  float z = 1.0f - 2.0f * u0;
+  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  float s, c;
+  sincospif(2.0f * u1, &s, &c);
+  return f3(r * c, r * s, z);
+}
+
+// ---------------------------------------------------------------------------------------
+struct Hit {
+  float t;
+  uint32_t ref;  // REF_NONE = miss
+};
+
+// sphere::hit (sphere.hpp:47-93) in a cancellation-free fp32 form: with l = oc - (b/a) d the
+// discriminant is a (r^2 - |l|^2) instead of b^2 - a c (both ~1e6 for the r=1000 ground).
+// `self`: the ray starts ON this sphere (it scattered there); the roots are then exactly 0
+// and -2b/a, which removes fp32 self-intersection without an epsilon.
+__device__ __forceinline__ float hit_sphere(float4 g0, float4 g1, float3 o, float3 d, float time, float tmin, float tmax, bool self) {
+  float3 c = fma3(time, xyz(g1), xyz(g0));
+  float3 oc = o - c;
+  float a = dot(d, d);
+  float b = dot(oc, d);
+  float inv_a = __frcp_rn(a);
+  if (self) {
+    float t = -2.0f * b * inv_a;
+    return (t > tmin && t < tmax) ? t : -1.0f;
+  }
+  float3 l = fma3(-b * inv_a, d, oc);
+  float disc = fmaf(g0.w, g0.w, -dot(l, l));
+  if (disc < 0.0f) return -1.0f;
+  float s = sqrtf(a * disc);
+  float t = (-b - s) * inv_a;
+  if (!(t > tmin && t < tmax)) {  // interval::surrounds
+    t = (-b + s) * inv_a;
+    if (!(t > tmin && t < tmax)) return -1.0f;
+  }
+  return t;
+}
+
+// both roots (for medium boundaries); returns false when the line misses the sphere
+__device__ __forceinline__ bool sphere_roots(float4 g0, float4 g1, float3 o, float3 d, float time, float& r0, float& r1) {
+  float3 c = fma3(time, xyz(g1), xyz(g0));
+  float3 oc = o - c;
+  float a = dot(d, d);
+  float b = dot(oc, d);
+  float inv_a = __frcp_rn(a);
+  float3 l = fma3(-b * inv_a, d, oc);
+  float disc = fmaf(g0.w, g0.w, -dot(l, l));
+  if (disc < 0.0f) return false;
+  float s = sqrtf(a * disc);
+  r0 = (-b - s) * inv_a;
+  r1 = (-b + s) * inv_a;
+  return true;
+}
+
+// quad::hit (quad.hpp:44-94) with the interior test (:97-114) folded into two plane
+// equations: alpha = A.p + a0, beta = B.p + b0 (A = v x w, B = w x u precomputed on the host).
+__device__ __forceinline__ float hit_quad(float4 nD, float4 A, float4 B, float3 o, float3 d, float tmin, float tmax) {
+  float denom = dot(xyz(nD), d);
+  if (fabsf(denom) < 1e-8f) return -1.0f;
+  float t = __fdividef(nD.w - dot(xyz(nD), o), denom);
+  if (!(t >= tmin && t <= tmax)) return -1.0f;  // interval::contains
+  float3 p = fma3(t, d, o);
+  float alpha = dot(xyz(A), p) + A.w;
+  float beta = dot(xyz(B), p) + B.w;
+  if (!(alpha >= 0.0f && alpha <= 1.0f && beta >= 0.0f && beta <= 1.0f)) return -1.0f;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// BVH node access: the first `smem_nodes` nodes (breadth-first = top levels) live in shared
+// memory, the rest is read through the read-only path (L1/L2 resident: the arrays are tiny).
+struct NodeSource {
+  const float4* smem;
+  const float4* gmem;
+  int smem_nodes;
+};
+__device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
+  float4 dd;
+  if (idx < ns.smem_nodes) {
+    const float4* p = ns.smem + 4 * idx;
+    a = p[0], b = p[1], c = p[2], dd = p[3];
+  } else {
+    const float4* p = ns.gmem + 4 * idx;
+    a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), dd = __ldg(p + 3);
+  }
+  c0 = __float_as_int(dd.x);
+  c1 = __float_as_int(dd.y);
+}
+
+// constant_medium::hit for one medium: entry/exit over the boundary primitives,
+// then an exponential free-flight sample.  `u` is the uniform this medium owns for this ray.
+__device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float& t1, float& t2) {
+  const float INF = __int_as_float(0x7f800000);
+  t1 = INF;
+  // pass 1: boundary->hit(r, universe): the smallest crossing
+  for (int k = 0; k < m.n_bref; k++) {
+    uint32_t ref = __ldg(sc.medium_brefs + m.first_bref + k);
+    uint32_t idx = ref & 0x3FFFFFFFu;
+    if ((ref >> 30) == REF_SPHERE) {
+      float r0, r1;
+      if (sphere_roots(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, r0, r1)) t1 = fminf(t1, r0);
+    } else {
+      float t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, -INF, INF);
+      if (t != -1.0f) t1 = fminf(t1, t);
+    }
+  }
+  if (t1 == INF) return false;
+  // pass 2: boundary->hit(r, interval(t1 + 0.0001, inf)): the next crossing
+  const float lo = t1 + 0.0001f;
+  t2 = INF;
+  for (int k = 0; k < m.n_bref; k++) {
+    uint32_t ref = __ldg(sc.medium_brefs + m.first_bref + k);
+    uint32_t idx = ref & 0x3FFFFFFFu;
+    if ((ref >> 30) == REF_SPHERE) {
+      float r0, r1;
+      if (sphere_roots(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, r0, r1)) {
+        float t = r0 > lo ? r0 : (r1 > lo ? r1 : INF);
+        t2 = fminf(t2, t);
+      }
+    } else {
+      float t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, lo, INF);
+      if (t != -1.0f) t2 = fminf(t2, t);
+    }
+  }
+  return t2 != INF;
+}
+
+__device__ __forceinline__ float medium_sample(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float tmin, float tmax, float u) {
+  float t1, t2;
+  if (!medium_span(sc, m, o, d, time, t1, t2)) return -1.0f;
+  t1 = fmaxf(t1, tmin);
+  t2 = fminf(t2, tmax);
+  if (t1 >= t2) return -1.0f;
+  t1 = fmaxf(t1, 0.0f);
+  float len = sqrtf(dot(d, d));
+  float inside = (t2 - t1) * len;
+  float hit_distance = m.neg_inv_density * __logf(u);  // u == 0 -> +inf -> miss, as log(0) in the reference
+  if (!(hit_distance <= inside)) return -1.0f;
+  return t1 + hit_distance / len;
+}
+
+// Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2).
+struct MediumRng {
+  const PathKey* key;
+  uint32_t bounce;
+  uint32_t cached_stream;
+  uint4 cached;
+  __device__ __forceinline__ float get(int medium) {
+    uint32_t stream = 1u + (uint32_t(medium) >> 2);
+    if (stream != cached_stream) {
+      cached = rng_block(*key, bounce, stream);
+      cached_stream = stream;
+    }
+    uint32_t c = uint32_t(medium) & 3u;
+    uint32_t v = c == 0 ? cached.x : (c == 1 ? cached.y : (c == 2 ? cached.z : cached.w));
+    return u01(v);
+  }
+};
+
+constexpr int kStackDepth = 32;
+
+// world.hit(r, interval(tmin, tmax), rec): closest hit over the whole scene.
+//   skip_ref: the primitive the ray starts on (REF_NONE for camera rays / medium scatters).
+//   mrng == nullptr: media are transparent.
+__device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
+                                           uint32_t skip_ref, MediumRng* mrng) {
+  // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
+  float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
+                  fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+  float3 ood = o * inv;
+  Hit best{tmax, REF_NONE};
+  int stack[kStackDepth];
+  float stack_t[kStackDepth];
+  int sp = 0;
+  int cur = 0;
+  for (;;) {
+    if (cur >= 0) {
+      float4 a, b, c;
+      int c0, c1;
+      load_node(ns, cur, a, b, c, c0, c1);
+      // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
+      float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
+      float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
+      float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
+      float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+      float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
+      x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
+      y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
+      z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
+      float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+      float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
+      bool h0 = n0 <= f0, h1 = n1 <= f1;
+      if (h0 && h1) {
+        bool first0 = n0 <= n1;
+        if (sp < kStackDepth) {
+          stack[sp] = first0 ? c1 : c0;
+          stack_t[sp] = first0 ? n1 : n0;
+          sp++;
+        }
+        cur = first0 ? c0 : c1;
+        continue;
+      }
+      if (h0) { cur = c0; continue; }
+      if (h1) { cur = c1; continue; }
+    } else {
+      // leaf: ~cur = (first << 3) | (count - 1)
+      int code = ~cur;
+      int first = code >> 3, count = (code & 7) + 1;
+      for (int k = 0; k < count; k++) {
+        uint32_t ref = __ldg(sc.leaf_refs + first + k);
+        uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+        float t = -1.0f;
+        if (type == REF_SPHERE) {
+          t = hit_sphere(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, tmin, best.t, ref == skip_ref);
+        } else if (type == REF_QUAD) {
+          if (ref != skip_ref) t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, tmin, best.t);
+        } else if (ref != REF_NONE && mrng) {
+          const DMedium m = sc.media[idx];
+          t = medium_sample(sc, m, o, d, time, tmin, best.t, mrng->get(int(idx)));
+        }
+        if (t != -1.0f) best = Hit{t, ref};
+      }
+    }
+    // pop, skipping subtrees that start beyond the current closest hit
+    for (;;) {
+      if (sp == 0) return best;
+      sp--;
+      if (stack_t[sp] <= best.t) { cur = stack[sp]; break; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// textures (core/texture.hpp, core/perlin.hpp)
+__device__ __forceinline__ float perlin_noise(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {
+  float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  int i = int(fx), j = int(fy), k = int(fz);
+  float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+  int px[2] = {perm[i & 255], perm[(i + 1) & 255]};
+  int py[2] = {perm[256 + (j & 255)], perm[256 + ((j + 1) & 255)]};
+  int pz[2] = {perm[512 + (k & 255)], perm[512 + ((k + 1) & 255)]};
+  float accum = 0.0f;
+#pragma unroll
+  for (int di = 0; di < 2; di++)
+#pragma unroll
+    for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+      for (int dk = 0; dk < 2; dk++) {
+        float4 g = __ldg(vec + (px[di] ^ py[dj] ^ pz[dk]));
+        float wgt = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
+        accum = fmaf(wgt, g.x * (u - di) + g.y * (v - dj) + g.z * (w - dk), accum);
+      }
+  return accum;
+}
+
+__device__ __forceinline__ float perlin_turb(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {
+  float accum = 0.0f, weight = 1.0f;
+#pragma unroll 1
+  for (int i = 0; i < 7; i++) {  // noise.turb(p, 7), texture.hpp:150
+    accum = fmaf(weight, perlin_noise(vec, perm, p), accum);
+    weight *= 0.5f;
+    p = 2.0f * p;
+  }
+  return fabsf(accum);
+}
+
+// get_sphere_uv (sphere.hpp:100-111) from the OBJECT-space outward normal
+__device__ __forceinline__ float2 sphere_uv(float3 n) {
+  const float PI = 3.14159265358979323846f;
+  float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
+  float phi = atan2f(-n.z, n.x) + PI;
+  return make_float2(phi * (0.5f / PI), theta * (1.0f / PI));
+}
+
+__device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p) {
+#pragma unroll 1
+  for (int guard = 0; guard < 16; guard++) {
+    float4 t0 = __ldg(sc.textures + 2 * tex), t1 = __ldg(sc.textures + 2 * tex + 1);
+    int kind = __float_as_int(t1.x), a = __float_as_int(t1.y), b = __float_as_int(t1.z);
+    if (kind == TEX_SOLID) return xyz(t0);
+    if (kind == TEX_CHECKER) {  // texture.hpp:57-79 ; (sum % 2 == 0) == ((sum & 1) == 0) for negatives too
+      int s = int(floorf(t0.w * p.x)) + int(floorf(t0.w * p.y)) + int(floorf(t0.w * p.z));
+      tex = (s & 1) ? b : a;
+      continue;
+    }
+    if (kind == TEX_IMAGE) {  // texture.hpp:97-118 + rtw_stb_image.hpp:104-134
+      int4 im = __ldg(sc.images + a);
+      if (im.z <= 0) return f3(0.0f, 1.0f, 1.0f);
+      u = fminf(fmaxf(u, 0.0f), 1.0f);
+      v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+      int i = min(int(u * im.y), im.y - 1);
+      int j = min(int(v * im.z), im.z - 1);
+      uchar4 px = __ldg(sc.texels + im.x + j * im.y + i);
+      const float s = 1.0f / 255.0f;
+      return f3(s * px.x, s * px.y, s * px.z);
+    }
+    // TEX_NOISE: marble, texture.hpp:150
+    float turb = perlin_turb(sc.perlin_vec + 256 * a, sc.perlin_perm + 768 * a, p);
+    float g = 0.5f * (1.0f + sinf(fmaf(t0.w, p.z, 10.0f * turb)));
+    return f3(g, g, g);
+  }
+  return f3(0.0f, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------
+// surface reconstruction at the hit + material::emitted / material::scatter
+struct Surface {
+  float3 p, n;  // n already flipped against the ray (hit_record::set_face_normal)
+  float u, v;
+  bool front;
+  int material;
+};
+
+__device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, float3 o, float3 d, float time) {
+  Surface s;
+  uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
+  s.p = fma3(h.t, d, o);
+  s.u = s.v = 0.0f;
+  if (type == REF_SPHERE) {
+    float4 g0 = __ldg(sc.spheres + 2 * idx), g1 = __ldg(sc.spheres + 2 * idx + 1);
+    int2 meta = __ldg(sc.sph_meta + idx);
+    float3 c = fma3(time, xyz(g1), xyz(g0));
+    float3 outward = __frcp_rn(g0.w) * (s.p - c);
+    s.p = fma3(g0.w, outward, c);  // re-project onto the sphere: removes the O(t*eps) drift of o + t d
+    s.material = meta.x;
+    float4 m1 = __ldg(sc.materials + 2 * meta.x + 1);
+    if (__float_as_int(m1.z) & MATF_NEEDS_UV) {
+      float3 no = outward;
+      if (meta.y >= 0) {  // back to the instance's object space (inverse y-rotation)
+        float2 r = __ldg(sc.rotations + meta.y);
+        no = f3(r.y * outward.x - r.x * outward.z, outward.y, r.x * outward.x + r.y * outward.z);
+      }
+      float2 uv = sphere_uv(no);
+      s.u = uv.x, s.v = uv.y;
+    }
+    s.front = dot(d, outward) < 0.0f;
+    s.n = s.front ? outward : -outward;
+  } else if (type == REF_QUAD) {
+    float4 nD = __ldg(sc.quads + 3 * idx);
+    s.material = __ldg(sc.quad_mat + idx);
+    float4 m1 = __ldg(sc.materials + 2 * s.material + 1);
+    if (__float_as_int(m1.z) & MATF_NEEDS_UV) {
+      float4 A = __ldg(sc.quads + 3 * idx + 1), B = __ldg(sc.quads + 3 * idx + 2);
+      s.u = dot(xyz(A), s.p) + A.w;
+      s.v = dot(xyz(B), s.p) + B.w;
+    }
+    s.front = dot(d, xyz(nD)) < 0.0f;
+    s.n = s.front ? xyz(nD) : -xyz(nD);
+  } else {  // medium: arbitrary normal, front face
+    s.material = sc.media[idx].material;
+    s.n = f3(1.0f, 0.0f, 0.0f);
+    s.front = true;
+  }
+  return s;
+}
+
+// returns true when the path continues along (o, d); `emit` is material::emitted.
+__device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out) {
+  float4 m0 = __ldg(sc.materials + 2 * s.material), m1 = __ldg(sc.materials + 2 * s.material + 1);
+  int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
+  emit = f3(0.0f, 0.0f, 0.0f);
+  switch (kind) {
+    case MAT_LAMBERTIAN: {  // material.hpp:51-71
+      float3 dir = s.n + unit_vector_from(u01(rnd.x), u01(rnd.y));
+      if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
+      d_out = dir;
+      atten = texture_value(sc, tex, s.u, s.v, s.p);
+      return true;
+    }
+    case MAT_METAL: {  // material.hpp:86-106
+      float3 refl = fma3(-2.0f * dot(d_in, s.n), s.n, d_in);
+      d_out = fma3(m0.w, unit_vector_from(u01(rnd.x), u01(rnd.y)), normalize3(refl));
+      atten = xyz(m0);
+      return dot(d_out, s.n) > 0.0f;
+    }
+    case MAT_DIELECTRIC: {  // material.hpp:128-206
+      atten = f3(1.0f, 1.0f, 1.0f);
+      float ri = s.front ? __frcp_rn(m0.w) : m0.w;
+      float3 ud = normalize3(d_in);
+      float cos_t = fminf(-dot(ud, s.n), 1.0f);
+      float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+      bool reflect = ri * sin_t > 1.0f;
+      if (!reflect) {
+        float r0 = (1.0f - ri) / (1.0f + ri);
+        r0 *= r0;
+        float x = 1.0f - cos_t, x2 = x * x;
+        reflect = fmaf(1.0f - r0, x2 * x2 * x, r0) > u01(rnd.z);
+      }
+      if (reflect) {
+        d_out = fma3(-2.0f * dot(ud, s.n), s.n, ud);
+      } else {  // refract, vec3.hpp:216-226
+        float3 perp = ri * fma3(cos_t, s.n, ud);
+        float par = -sqrtf(fabsf(1.0f - dot(perp, perp)));
+        d_out = fma3(par, s.n, perp);
+      }
+      return true;
+    }
+    case MAT_LIGHT:  // material.hpp:223-240: emits on both faces, never scatters
+      emit = texture_value(sc, tex, s.u, s.v, s.p);
+      return false;
+    default:  // MAT_ISOTROPIC, SURVEY B.3
+      d_out = unit_vector_from(u01(rnd.x), u01(rnd.y));
+      atten = texture_value(sc, tex, s.u, s.v, s.p);
+      return true;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 exact predicates: every operation is an explicit IEEE round-to-nearest intrinsic, so
+// nvcc cannot contract a*b+c into an FMA and the results round exactly like the reference
+// built by g++ for x86-64 (which has no FMA at the baseline ISA).
+struct sd {
+  double v;
+};
+__device__ __forceinline__ sd S(double v) { return sd{v}; }
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd{__dadd_rn(a.v, b.v)}; }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd{__dsub_rn(a.v, b.v)}; }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd{__dmul_rn(a.v, b.v)}; }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd{__ddiv_rn(a.v, b.v)}; }
+__device__ __forceinline__ sd operator-(sd a) { return sd{-a.v}; }
+struct sv {
+  sd x, y, z;
+};
+__device__ __forceinline__ sv SV(const double* p) { return sv{S(p[0]), S(p[1]), S(p[2])}; }
+__device__ __forceinline__ sv operator+(sv a, sv b) { return sv{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ sv operator-(sv a, sv b) { return sv{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ sv operator-(sv a) { return sv{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ sv operator*(sd t, sv v) { return sv{t * v.x, t * v.y, t * v.z}; }
+__device__ __forceinline__ sd sdot(sv a, sv b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // vec3.hpp:138-141, left to right
+__device__ __forceinline__ sv scross(sv a, sv b) { return sv{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+struct XRay {
+  sv o, d;
+  sd tm;
+};
+struct XRec {
+  sd t;
+  sv n;
+  bool front;
+};
+
+// translate::hit / rotate_y::hit ray transforms, outermost wrapper first
+__device__ __forceinline__ XRay exact_to_object(const DeviceScene& sc, int chain, XRay r) {
+  int2 ch = sc.xchains[chain];
+  for (int k = 0; k < ch.y; k++) {
+    const XOp& op = sc.xops[ch.x + k];
+    if (op.kind == 0) {  // hittable.hpp:89
+      r.o = r.o - SV(op.a);
+    } else {
+      sd s = S(op.a[0]), c = S(op.a[1]);
+      r.o = sv{(c * r.o.x) - (s * r.o.z), r.o.y, (s * r.o.x) + (c * r.o.z)};
+      r.d = sv{(c * r.d.x) - (s * r.d.z), r.d.y, (s * r.d.x) + (c * r.d.z)};
+    }
+  }
+  return r;
+}
+// ... and rec.normal back to world space, innermost wrapper first (translate leaves it alone)
+__device__ __forceinline__ sv exact_normal_to_world(const DeviceScene& sc, int chain, sv n) {
+  int2 ch = sc.xchains[chain];
+  for (int k = ch.y - 1; k >= 0; k--) {
+    const XOp& op = sc.xops[ch.x + k];
+    if (op.kind == 1) {
+      sd s = S(op.a[0]), c = S(op.a[1]);
+      n = sv{(c * n.x) + (s * n.z), n.y, (-s * n.x) + (c * n.z)};
+    }
+  }
+  return n;
+}
+
+// sphere::hit, sphere.hpp:47-93, operation for operation
+__device__ __forceinline__ bool exact_sphere(const DeviceScene& sc, const XSphere& q, const XRay& rw, double tmin, double tmax, XRec& rec) {
+  XRay r = exact_to_object(sc, q.chain, rw);
+  sv cc = SV(q.c) + r.tm * SV(q.dc);  // center.at(r.time())
+  sv oc = r.o - cc;
+  sd a = sdot(r.d, r.d);
+  sd half_b = sdot(oc, r.d);
+  sd c = sdot(oc, oc) - S(q.r) * S(q.r);
+  sd disc = half_b * half_b - a * c;
+  if (disc.v < 0) return false;
+  sd sq = S(__dsqrt_rn(disc.v));
+  sd root = (-half_b - sq) / a;
+  if (!(tmin < root.v && root.v < tmax)) {
+    root = (-half_b + sq) / a;
+    if (!(tmin < root.v && root.v < tmax)) return false;
+  }
+  rec.t = root;
+  sv p = r.o + root * r.d;
+  sv outward = (S(1.0) / S(q.r)) * (p - cc);
+  rec.front = sdot(r.d, outward).v < 0;
+  sv n = rec.front ? outward : -outward;
+  rec.n = exact_normal_to_world(sc, q.chain, n);
+  return true;
+}
+
+// quad::hit + is_interior, quad.hpp:44-114
+__device__ __forceinline__ bool exact_quad(const DeviceScene& sc, const XQuad& q, const XRay& rw, double tmin, double tmax, XRec& rec) {
+  XRay r = exact_to_object(sc, q.chain, rw);
+  sv normal = SV(q.n);
+  sd denom = sdot(normal, r.d);
+  if (fabs(denom.v) < 1e-8) return false;
+  sd t = (S(q.D) - sdot(normal, r.o)) / denom;
+  if (!(tmin <= t.v && t.v <= tmax)) return false;
+  sv ip = r.o + t * r.d;
+  sv hp = ip - SV(q.Q);
+  sd alpha = sdot(SV(q.w), scross(hp, SV(q.v)));
+  sd beta = sdot(SV(q.w), scross(SV(q.u), hp));
+  if (!(0.0 <= alpha.v && alpha.v <= 1.0) || !(0.0 <= beta.v && beta.v <= 1.0)) return false;
+  rec.t = t;
+  rec.front = sdot(r.d, normal).v < 0;
+  sv n = rec.front ? normal : -normal;
+  rec.n = exact_normal_to_world(sc, q.chain, n);
+  return true;
+}
+
+}  // namespace rtb200

@@ -1,0 +1,995 @@
+// rtb200_host.hpp — host-side mirror of the reference's C++ scene-building API.
+//
+// Same class names, constructors and public members as jooo0922/raytracing-practice
+// (SURVEY.md Appendix D), so scene code such as the reference's src/main.cpp compiles
+// unchanged with `-I raytracing-practice_b200/host`.  The difference: these classes only
+// RECORD parameters.  There is no CPU intersection / shading code here — camera::render
+// flattens the shared_ptr graph into the POD arrays of include/rt_b200.h and hands them
+// to the CUDA library (rt_upload_scene / rt_render / rt_download).  No CPU fallback.
+//
+// Arithmetic that decides scene CONTENT (rand() draws, bounding boxes, BVH topology) is
+// done in double with the reference's operation order, so that the flattened scene is
+// bit-identical to what the reference would have built from the same rand() stream.
+#ifndef RTB200_HOST_HPP
+#define RTB200_HOST_HPP
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "rt_b200.h"
+#include "rtb200_jpeg.hpp"
+
+// ---------------------------------------------------------------------------------------
+// common/rtweekend.hpp:14-39
+const double infinity = std::numeric_limits<double>::infinity();
+const double pi = 3.1415926535897932385;
+
+inline double degrees_to_radians(double degrees) { return degrees * pi / 180.0f; }
+
+// int / float division exactly as rtweekend.hpp:26 (24-bit granularity, may return 1.0).
+inline double random_double() { return std::rand() / (RAND_MAX + 1.0f); }
+inline double random_double(double lo, double hi) { return lo + (hi - lo) * random_double(); }
+inline int random_int(int lo, int hi) { return int(random_double(lo, hi + 1)); }
+
+// ---------------------------------------------------------------------------------------
+// common/vec3.hpp:8-226.  Division is "multiply by 1/t" as in the reference (:55,:133).
+class vec3 {
+ public:
+  double e[3];
+  vec3() : e{0, 0, 0} {}
+  vec3(double a, double b, double c) : e{a, b, c} {}
+  double x() const { return e[0]; }
+  double y() const { return e[1]; }
+  double z() const { return e[2]; }
+  vec3 operator-() const { return vec3(-e[0], -e[1], -e[2]); }
+  double operator[](int i) const { return e[i]; }
+  double& operator[](int i) { return e[i]; }
+  vec3& operator+=(const vec3& o) {
+    for (int i = 0; i < 3; i++) e[i] += o.e[i];
+    return *this;
+  }
+  vec3& operator*=(double t) {
+    for (int i = 0; i < 3; i++) e[i] *= t;
+    return *this;
+  }
+  vec3& operator/=(double t) { return *this *= 1 / t; }
+  double length_squared() const { return e[0] * e[0] + e[1] * e[1] + e[2] * e[2]; }
+  double length() const { return std::sqrt(length_squared()); }
+  bool near_zero() const {  // the intended test (the reference's :76 has a paren slip)
+    const double s = 1e-8;
+    return std::fabs(e[0]) < s && std::fabs(e[1]) < s && std::fabs(e[2]) < s;
+  }
+  // Same expression shape as vec3.hpp:82,87 so the compiler orders the three rand()
+  // draws the same way it does for the reference (g++: right to left).
+  static vec3 random() { return vec3(random_double(), random_double(), random_double()); }
+  static vec3 random(double lo, double hi) {
+    return vec3(random_double(lo, hi), random_double(lo, hi), random_double(lo, hi));
+  }
+};
+using point3 = vec3;
+using color = vec3;
+
+inline std::ostream& operator<<(std::ostream& o, const vec3& v) {
+  return o << v.e[0] << ' ' << v.e[1] << ' ' << v.e[2];
+}
+inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.e[0] + b.e[0], a.e[1] + b.e[1], a.e[2] + b.e[2]); }
+inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.e[0] - b.e[0], a.e[1] - b.e[1], a.e[2] - b.e[2]); }
+inline vec3 operator*(const vec3& a, const vec3& b) { return vec3(a.e[0] * b.e[0], a.e[1] * b.e[1], a.e[2] * b.e[2]); }
+inline vec3 operator*(double t, const vec3& v) { return vec3(t * v.e[0], t * v.e[1], t * v.e[2]); }
+inline vec3 operator*(const vec3& v, double t) { return t * v; }
+inline vec3 operator/(vec3 v, double t) { return (1 / t) * v; }
+inline double dot(const vec3& a, const vec3& b) { return a.e[0] * b.e[0] + a.e[1] * b.e[1] + a.e[2] * b.e[2]; }
+inline vec3 cross(const vec3& a, const vec3& b) {
+  return vec3(a.e[1] * b.e[2] - a.e[2] * b.e[1], a.e[2] * b.e[0] - a.e[0] * b.e[2],
+              a.e[0] * b.e[1] - a.e[1] * b.e[0]);
+}
+inline vec3 unit_vector(vec3 v) { return v / v.length(); }
+inline vec3 random_in_unit_disk() {
+  for (;;) {
+    vec3 p = vec3(random_double(-1.0f, 1.0f), random_double(-1.0f, 1.0f), 0.0f);
+    if (p.length_squared() < 1.0f) return p;
+  }
+}
+inline vec3 random_unit_vector() {
+  for (;;) {
+    vec3 p = vec3::random(-1, 1);
+    double l2 = p.length_squared();
+    if (1e-160 < l2 && l2 <= 1) return p / std::sqrt(l2);
+  }
+}
+inline vec3 random_on_hemisphere(const vec3& n) {
+  vec3 s = random_unit_vector();
+  return dot(s, n) > 0.0f ? s : -s;
+}
+inline vec3 reflect(const vec3& v, const vec3& n) { return v - 2.0f * dot(v, n) * n; }
+inline vec3 refract(const vec3& uv, const vec3& n, double eta_ratio) {
+  double c = std::fmin(dot(-uv, n), 1.0f);
+  vec3 perp = eta_ratio * (uv + c * n);
+  vec3 par = -std::sqrt(std::fabs(1.0f - perp.length_squared())) * n;
+  return perp + par;
+}
+
+// common/ray.hpp:7-32
+class ray {
+ public:
+  ray() {}
+  ray(const point3& o, const vec3& d, double t) : orig(o), dir(d), tm(t) {}
+  ray(const point3& o, const vec3& d) : ray(o, d, 0.0f) {}
+  point3 origin() const { return orig; }
+  vec3 direction() const { return dir; }
+  double time() const { return tm; }
+  point3 at(double t) const { return orig + t * dir; }
+
+ private:
+  point3 orig;
+  vec3 dir;
+  double tm = 0;
+};
+
+// common/interval.hpp:10-80
+class interval {
+ public:
+  double min, max;
+  interval() : min(+infinity), max(-infinity) {}
+  interval(double lo, double hi) : min(lo), max(hi) {}
+  interval(const interval& a, const interval& b)
+      : min(a.min <= b.min ? a.min : b.min), max(a.max >= b.max ? a.max : b.max) {}
+  double size() const { return max - min; }
+  bool contains(double x) const { return min <= x && x <= max; }
+  bool surrounds(double x) const { return min < x && x < max; }
+  double clamp(double x) const { return x < min ? min : (x > max ? max : x); }
+  interval expand(double delta) const {
+    double pad = delta / 2.0f;
+    return interval(min - pad, max + pad);
+  }
+  static const interval empty, universe;
+};
+inline interval operator+(const interval& i, double d) { return interval(i.min + d, i.max + d); }
+inline interval operator+(double d, const interval& i) { return i + d; }
+// One definition per program in C++11 (the reference's rule too: the whole API is a
+// single-TU header set, interval.hpp:79-80); `inline` variables from C++17 on.
+#if __cplusplus >= 201703L
+#define RTB200_INLINE_VAR inline
+#else
+#define RTB200_INLINE_VAR
+#endif
+RTB200_INLINE_VAR const interval interval::empty = interval(+infinity, -infinity);
+RTB200_INLINE_VAR const interval interval::universe = interval(-infinity, +infinity);
+
+// common/color.hpp:14-58
+inline double linear_to_gamma(double x) { return x > 0.0f ? std::sqrt(x) : 0.0f; }
+inline void write_color(std::ostream& out, const color& c) {
+  const interval intensity(0.000f, 0.999f);
+  int r = int(256 * intensity.clamp(linear_to_gamma(c.x())));
+  int g = int(256 * intensity.clamp(linear_to_gamma(c.y())));
+  int b = int(256 * intensity.clamp(linear_to_gamma(c.z())));
+  out << r << ' ' << g << ' ' << b << '\n';
+}
+
+// ---------------------------------------------------------------------------------------
+// accelerator/aabb.hpp:12-173 — only construction (padding rules) is needed on the host.
+class aabb {
+ public:
+  interval x, y, z;
+  aabb() {}
+  aabb(const interval& ix, const interval& iy, const interval& iz) : x(ix), y(iy), z(iz) { pad_to_minimums(); }
+  aabb(const point3& a, const point3& b) {
+    x = (a[0] <= b[0]) ? interval(a[0], b[0]) : interval(b[0], a[0]);
+    y = (a[1] <= b[1]) ? interval(a[1], b[1]) : interval(b[1], a[1]);
+    z = (a[2] <= b[2]) ? interval(a[2], b[2]) : interval(b[2], a[2]);
+    pad_to_minimums();
+  }
+  aabb(const aabb& a, const aabb& b) : x(a.x, b.x), y(a.y, b.y), z(a.z, b.z) {}  // no re-pad (:42-48)
+  const interval& axis_interval(int n) const { return n == 1 ? y : (n == 2 ? z : x); }
+  int longest_axis() const {  // ties go to the later axis (:116-127)
+    if (x.size() > y.size()) return x.size() > z.size() ? 0 : 2;
+    return y.size() > z.size() ? 1 : 2;
+  }
+  static const aabb empty, universe;
+
+ private:
+  void pad_to_minimums() {
+    const double delta = 0.0001;
+    if (x.size() < delta) x = x.expand(delta);
+    if (y.size() < delta) y = y.expand(delta);
+    if (z.size() < delta) z = z.expand(delta);
+  }
+};
+RTB200_INLINE_VAR const aabb aabb::empty = aabb(interval::empty, interval::empty, interval::empty);
+RTB200_INLINE_VAR const aabb aabb::universe = aabb(interval::universe, interval::universe, interval::universe);
+inline aabb operator+(const aabb& b, const vec3& o) { return aabb(b.x + o.x(), b.y + o.y(), b.z + o.z()); }
+inline aabb operator+(const vec3& o, const aabb& b) { return b + o; }
+
+// ---------------------------------------------------------------------------------------
+// The flattener: walks the graph once and fills the POD arrays of include/rt_b200.h.
+namespace rtb200 {
+
+class scene_builder {
+ public:
+  std::vector<rt_hittable> hittables;
+  std::vector<int32_t> child_index;
+  std::vector<rt_material> materials;
+  std::vector<rt_texture> textures;
+  std::vector<rt_image> images;
+  std::vector<rt_perlin> perlins;
+  std::vector<std::vector<uint8_t>> image_storage;
+  int32_t n_prims = 0;
+  int32_t root = -1;
+
+  // memoised by object address: shared nodes are emitted (and numbered) once.
+  std::map<const void*, int32_t> seen_hittable, seen_material, seen_texture;
+
+  int32_t new_hittable(const void* key, int32_t kind, const aabb& box) {
+    rt_hittable h;
+    std::memset(&h, 0, sizeof h);
+    h.kind = kind;
+    h.material = h.child0 = h.child1 = h.prim_id = -1;
+    h.bbox[0] = box.x.min, h.bbox[1] = box.x.max;
+    h.bbox[2] = box.y.min, h.bbox[3] = box.y.max;
+    h.bbox[4] = box.z.min, h.bbox[5] = box.z.max;
+    hittables.push_back(h);
+    int32_t id = int32_t(hittables.size()) - 1;
+    seen_hittable[key] = id;
+    return id;
+  }
+
+  rt_scene_desc desc() const {
+    rt_scene_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.abi_version = RT_B200_ABI_VERSION;
+    d.root = root;
+    d.n_hittables = int32_t(hittables.size());
+    d.n_child_index = int32_t(child_index.size());
+    d.n_materials = int32_t(materials.size());
+    d.n_textures = int32_t(textures.size());
+    d.n_images = int32_t(images.size());
+    d.n_perlins = int32_t(perlins.size());
+    d.n_prims = n_prims;
+    d.hittables = hittables.data();
+    d.child_index = child_index.data();
+    d.materials = materials.data();
+    d.textures = textures.data();
+    d.images = images.data();
+    d.perlins = perlins.data();
+    return d;
+  }
+};
+
+[[noreturn]] inline void no_cpu_path(const char* what) {
+  std::fprintf(stderr,
+               "rtb200: %s was called on the host, but this build has no CPU rendering path "
+               "(the hot path runs on the GPU behind camera::render).\n",
+               what);
+  std::abort();
+}
+
+}  // namespace rtb200
+
+// ---------------------------------------------------------------------------------------
+// core/rtw_stb_image.hpp:28-178.  stb_image is not vendored by the reference (FetchContent,
+// _cmake/stb.cmake:6-9) and is not available offline, so loading goes through our own
+// baseline-JPEG decoder (rtb200_jpeg.hpp); binary PPM (P6) is accepted too.  The
+// post-decode conventions are stb's + the reference's: linearise with pow(b/255, 2.2)
+// (stb's stbi_loadf LDR->float default) then re-quantise with float_to_byte (:137-150).
+class rtw_image {
+ public:
+  rtw_image() {}
+  rtw_image(const char* image_filename) {
+    std::string filename(image_filename);
+    const char* imagedir = std::getenv("RTW_IMAGES");
+    if (imagedir && load(std::string(imagedir) + "/" + image_filename)) return;
+    if (load(filename)) return;
+    std::string prefix = "images/";
+    for (int up = 0; up < 7; up++) {  // images/, ../images/, ... six levels (:48-61)
+      if (load(prefix + filename)) return;
+      prefix = "../" + prefix;
+    }
+    std::cerr << "ERROR: Could not load image file '" << image_filename << "'\n";
+  }
+  bool load(const std::string& filename) {
+    std::vector<uint8_t> rgb;
+    int w = 0, h = 0;
+    if (!rtb200::load_image_rgb8(filename, rgb, w, h)) return false;
+    image_width = w, image_height = h;
+    bdata.resize(rgb.size());
+    for (size_t i = 0; i < rgb.size(); i++) {
+      float f = float(std::pow(rgb[i] / 255.0f, 2.2f));  // stbi__ldr_to_hdr, gamma 2.2, scale 1
+      bdata[i] = float_to_byte(f);
+    }
+    return true;
+  }
+  int width() const { return bdata.empty() ? 0 : image_width; }
+  int height() const { return bdata.empty() ? 0 : image_height; }
+  const unsigned char* pixel_data(int px, int py) const {
+    static unsigned char magenta[] = {255, 0, 255};
+    if (bdata.empty()) return magenta;
+    px = clamp(px, 0, image_width);
+    py = clamp(py, 0, image_height);
+    return bdata.data() + size_t(py) * image_width * 3 + size_t(px) * 3;
+  }
+  const std::vector<uint8_t>& bytes() const { return bdata; }
+
+ private:
+  static int clamp(int v, int lo, int hi) { return v < lo ? lo : (v < hi ? v : hi - 1); }
+  static unsigned char float_to_byte(float v) {
+    if (v <= 0.0f) return 0;
+    if (v >= 1.0f) return 255;
+    return static_cast<unsigned char>(256.0f * v);
+  }
+  std::vector<uint8_t> bdata;
+  int image_width = 0, image_height = 0;
+};
+
+// core/perlin.hpp:9-31,162-188 — table construction only (draws rand() exactly as the
+// reference: 256 x unit_vector(vec3::random(-1,1)) then three Fisher-Yates permutes).
+class perlin {
+ public:
+  static const int point_count = 256;
+  perlin() {
+    for (int i = 0; i < point_count; i++) randvec[i] = unit_vector(vec3::random(-1.0f, 1.0f));
+    generate_perm(perm_x);
+    generate_perm(perm_y);
+    generate_perm(perm_z);
+  }
+  double noise_perlin(const point3&) const { rtb200::no_cpu_path("perlin::noise_perlin"); }
+  double turb(const point3&, int) const { rtb200::no_cpu_path("perlin::turb"); }
+  void export_tables(rt_perlin& out) const {
+    for (int i = 0; i < point_count; i++) {
+      for (int c = 0; c < 3; c++) out.randvec[i][c] = randvec[i][c];
+      out.perm_x[i] = perm_x[i], out.perm_y[i] = perm_y[i], out.perm_z[i] = perm_z[i];
+    }
+  }
+
+ private:
+  static void generate_perm(int* p) {
+    for (int i = 0; i < point_count; i++) p[i] = i;
+    for (int i = point_count - 1; i > 0; i--) {
+      int target = random_int(0, i);
+      if (target > i) target = i;  // random_double() can return exactly 1.0:
+                                   // the reference would read out of bounds here.
+      std::swap(p[i], p[target]);
+    }
+  }
+  vec3 randvec[point_count];
+  int perm_x[point_count], perm_y[point_count], perm_z[point_count];
+};
+
+// core/texture.hpp:11-156
+class texture {
+ public:
+  virtual ~texture() = default;
+  virtual color value(double, double, const point3&) const { rtb200::no_cpu_path("texture::value"); }
+  virtual int32_t flatten(rtb200::scene_builder& b) const = 0;
+
+ protected:
+  static int32_t emit(rtb200::scene_builder& b, const void* key, const rt_texture& t) {
+    b.textures.push_back(t);
+    return b.seen_texture[key] = int32_t(b.textures.size()) - 1;
+  }
+  static rt_texture blank(int32_t kind) {
+    rt_texture t;
+    std::memset(&t, 0, sizeof t);
+    t.kind = kind;
+    t.even = t.odd = t.image = t.perlin = -1;
+    return t;
+  }
+};
+
+inline int32_t rtb200_flatten_texture(rtb200::scene_builder& b, const texture* t) {
+  auto it = b.seen_texture.find(t);
+  return it != b.seen_texture.end() ? it->second : t->flatten(b);
+}
+
+class solid_color : public texture {
+ public:
+  solid_color(const color& a) : albedo(a) {}
+  solid_color(double r, double g, double bl) : solid_color(color(r, g, bl)) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    rt_texture t = blank(RT_T_SOLID);
+    for (int c = 0; c < 3; c++) t.color[c] = albedo[c];
+    return emit(b, this, t);
+  }
+
+ private:
+  color albedo;
+};
+
+class checker_texture : public texture {
+ public:
+  checker_texture(double scale, std::shared_ptr<texture> e, std::shared_ptr<texture> o)
+      : inv_scale(1.0f / scale), even(e), odd(o) {}
+  checker_texture(double scale, const color& c1, const color& c2)
+      : checker_texture(scale, std::make_shared<solid_color>(c1), std::make_shared<solid_color>(c2)) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    rt_texture t = blank(RT_T_CHECKER);
+    t.scale = inv_scale;
+    t.even = rtb200_flatten_texture(b, even.get());
+    t.odd = rtb200_flatten_texture(b, odd.get());
+    return emit(b, this, t);
+  }
+
+ private:
+  double inv_scale;
+  std::shared_ptr<texture> even, odd;
+};
+
+class image_texture : public texture {
+ public:
+  image_texture(const char* filename) : image(filename) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    rt_texture t = blank(RT_T_IMAGE);
+    b.image_storage.push_back(image.bytes());
+    rt_image im;
+    im.width = image.width();
+    im.height = image.height();
+    im.rgb = nullptr;  // patched after all storage is final (vector moves): see finalize()
+    b.images.push_back(im);
+    t.image = int32_t(b.images.size()) - 1;
+    return emit(b, this, t);
+  }
+
+ private:
+  rtw_image image;
+};
+
+class noise_texture : public texture {
+ public:
+  noise_texture(double s) : scale(s) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    rt_texture t = blank(RT_T_NOISE);
+    t.scale = scale;
+    rt_perlin p;
+    noise.export_tables(p);
+    b.perlins.push_back(p);
+    t.perlin = int32_t(b.perlins.size()) - 1;
+    return emit(b, this, t);
+  }
+
+ private:
+  perlin noise;
+  double scale;
+};
+
+// ---------------------------------------------------------------------------------------
+// hittable/hittable.hpp:16-50
+class material;
+class hit_record {
+ public:
+  point3 p;
+  vec3 normal;
+  std::shared_ptr<material> mat;
+  double t, u, v;
+  bool front_face;
+  void set_face_normal(const ray& r, const vec3& outward_normal) {
+    front_face = dot(r.direction(), outward_normal) < 0;
+    normal = front_face ? outward_normal : -outward_normal;
+  }
+};
+
+// core/material.hpp:21-240 (+ isotropic)
+class material {
+ public:
+  virtual ~material() = default;
+  virtual color emitted(double, double, const point3&) const { rtb200::no_cpu_path("material::emitted"); }
+  virtual bool scatter(const ray&, const hit_record&, color&, ray&) const { rtb200::no_cpu_path("material::scatter"); }
+  virtual int32_t flatten(rtb200::scene_builder& b) const = 0;
+
+ protected:
+  static int32_t emit(rtb200::scene_builder& b, const void* key, int32_t kind, int32_t tex, const color& albedo,
+                      double fuzz, double ior) {
+    rt_material m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = kind;
+    m.texture = tex;
+    for (int c = 0; c < 3; c++) m.albedo[c] = albedo[c];
+    m.fuzz = fuzz;
+    m.ior = ior;
+    b.materials.push_back(m);
+    return b.seen_material[key] = int32_t(b.materials.size()) - 1;
+  }
+};
+
+inline int32_t rtb200_flatten_material(rtb200::scene_builder& b, const material* m) {
+  auto it = b.seen_material.find(m);
+  return it != b.seen_material.end() ? it->second : m->flatten(b);
+}
+
+class lambertian : public material {
+ public:
+  lambertian(const color& albedo) : tex(std::make_shared<solid_color>(albedo)) {}
+  lambertian(std::shared_ptr<texture> t) : tex(t) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    return emit(b, this, RT_M_LAMBERTIAN, rtb200_flatten_texture(b, tex.get()), color(), 0, 0);
+  }
+
+ private:
+  std::shared_ptr<texture> tex;
+};
+
+class metal : public material {
+ public:
+  metal(const color& a, double f) : albedo(a), fuzz(f < 1.0f ? f : 1.0f) {}
+  int32_t flatten(rtb200::scene_builder& b) const override { return emit(b, this, RT_M_METAL, -1, albedo, fuzz, 0); }
+
+ private:
+  color albedo;
+  double fuzz;
+};
+
+class dielectric : public material {
+ public:
+  dielectric(double ri) : refraction_index(ri) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    return emit(b, this, RT_M_DIELECTRIC, -1, color(), 0, refraction_index);
+  }
+
+ private:
+  double refraction_index;
+};
+
+class diffuse_light : public material {
+ public:
+  diffuse_light(std::shared_ptr<texture> t) : tex(t) {}
+  diffuse_light(const color& emit_color) : tex(std::make_shared<solid_color>(emit_color)) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    return emit(b, this, RT_M_DIFFUSE_LIGHT, rtb200_flatten_texture(b, tex.get()), color(), 0, 0);
+  }
+
+ private:
+  std::shared_ptr<texture> tex;
+};
+
+class isotropic : public material {
+ public:
+  isotropic(const color& albedo) : tex(std::make_shared<solid_color>(albedo)) {}
+  isotropic(std::shared_ptr<texture> t) : tex(t) {}
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    return emit(b, this, RT_M_ISOTROPIC, rtb200_flatten_texture(b, tex.get()), color(), 0, 0);
+  }
+
+ private:
+  std::shared_ptr<texture> tex;
+};
+
+// ---------------------------------------------------------------------------------------
+class hittable {
+ public:
+  virtual ~hittable() = default;
+  virtual bool hit(const ray&, interval, hit_record&) const { rtb200::no_cpu_path("hittable::hit"); }
+  virtual aabb bounding_box() const = 0;
+  // A user subclass that is not one of the known concrete types cannot be flattened:
+  // fail loudly rather than silently dropping geometry (SURVEY.md Appendix D note).
+  virtual int32_t flatten(rtb200::scene_builder&) const {
+    std::fprintf(stderr, "rtb200: unknown hittable subclass cannot be uploaded to the GPU\n");
+    std::abort();
+  }
+};
+
+inline int32_t rtb200_flatten_hittable(rtb200::scene_builder& b, const hittable* h) {
+  auto it = b.seen_hittable.find(h);
+  return it != b.seen_hittable.end() ? it->second : h->flatten(b);
+}
+
+// hittable/hittable.hpp:74-117
+class translate : public hittable {
+ public:
+  translate(std::shared_ptr<hittable> obj, const vec3& off) : object(obj), offset(off) {
+    bbox = object->bounding_box() + offset;
+  }
+  aabb bounding_box() const override { return bbox; }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_TRANSLATE, bbox);
+    for (int c = 0; c < 3; c++) b.hittables[id].p[c] = offset[c];
+    int32_t child = rtb200_flatten_hittable(b, object.get());
+    b.hittables[id].child0 = child;
+    return id;
+  }
+
+ private:
+  std::shared_ptr<hittable> object;
+  vec3 offset;
+  aabb bbox;
+};
+
+// Not in the reference: "The Next Week" rotate_y.
+class rotate_y : public hittable {
+ public:
+  rotate_y(std::shared_ptr<hittable> obj, double angle) : object(obj), angle_degrees(angle) {
+    double radians = degrees_to_radians(angle);
+    sin_theta = std::sin(radians);
+    cos_theta = std::cos(radians);
+    bbox = object->bounding_box();
+    point3 lo(infinity, infinity, infinity), hi(-infinity, -infinity, -infinity);
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++)
+        for (int k = 0; k < 2; k++) {
+          double px = i * bbox.x.max + (1 - i) * bbox.x.min;
+          double py = j * bbox.y.max + (1 - j) * bbox.y.min;
+          double pz = k * bbox.z.max + (1 - k) * bbox.z.min;
+          double nx = cos_theta * px + sin_theta * pz;
+          double nz = -sin_theta * px + cos_theta * pz;
+          vec3 corner(nx, py, nz);
+          for (int c = 0; c < 3; c++) {
+            lo[c] = std::fmin(lo[c], corner[c]);
+            hi[c] = std::fmax(hi[c], corner[c]);
+          }
+        }
+    bbox = aabb(lo, hi);
+  }
+  aabb bounding_box() const override { return bbox; }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_ROTATE_Y, bbox);
+    b.hittables[id].p[0] = angle_degrees;
+    b.hittables[id].p[1] = sin_theta;
+    b.hittables[id].p[2] = cos_theta;
+    int32_t child = rtb200_flatten_hittable(b, object.get());
+    b.hittables[id].child0 = child;
+    return id;
+  }
+
+ private:
+  std::shared_ptr<hittable> object;
+  double angle_degrees, sin_theta, cos_theta;
+  aabb bbox;
+};
+
+// hittable/hittable_list.hpp:21-76
+class hittable_list : public hittable {
+ public:
+  std::vector<std::shared_ptr<hittable>> objects;
+  hittable_list() {}
+  hittable_list(std::shared_ptr<hittable> object) { add(object); }
+  void clear() { objects.clear(); }
+  void add(std::shared_ptr<hittable> object) {
+    objects.push_back(object);
+    bbox = aabb(bbox, object->bounding_box());
+  }
+  aabb bounding_box() const override { return bbox; }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_LIST, bbox);
+    std::vector<int32_t> kids;
+    for (const auto& o : objects) kids.push_back(rtb200_flatten_hittable(b, o.get()));
+    b.hittables[id].child0 = int32_t(b.child_index.size());
+    b.hittables[id].child1 = int32_t(kids.size());
+    b.child_index.insert(b.child_index.end(), kids.begin(), kids.end());
+    return id;
+  }
+
+ private:
+  aabb bbox;
+};
+
+// hittable/sphere.hpp:7-119
+class sphere : public hittable {
+ public:
+  sphere(point3 static_center, double r, std::shared_ptr<material> m)
+      : center(static_center, vec3(0.0f, 0.0f, 0.0f)), radius(r), mat(m) {
+    vec3 rvec(radius, radius, radius);
+    bbox = aabb(static_center - rvec, static_center + rvec);
+  }
+  sphere(point3 c1, point3 c2, double r, std::shared_ptr<material> m) : center(c1, c2 - c1), radius(r), mat(m) {
+    vec3 rvec(radius, radius, radius);
+    aabb box1(center.at(0.0f) - rvec, center.at(0.0f) + rvec);
+    aabb box2(center.at(1.0f) - rvec, center.at(1.0f) + rvec);
+    bbox = aabb(box1, box2);
+  }
+  aabb bounding_box() const override { return bbox; }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_SPHERE, bbox);
+    b.hittables[id].prim_id = b.n_prims++;
+    for (int c = 0; c < 3; c++) {
+      b.hittables[id].p[c] = center.origin()[c];
+      b.hittables[id].p[3 + c] = center.direction()[c];
+    }
+    b.hittables[id].p[6] = radius;
+    int32_t m = rtb200_flatten_material(b, mat.get());
+    b.hittables[id].material = m;
+    return id;
+  }
+
+ private:
+  ray center;
+  double radius;
+  std::shared_ptr<material> mat;
+  aabb bbox;
+};
+
+// hittable/quad.hpp:8-159
+class quad : public hittable {
+ public:
+  quad(const point3& q, const vec3& eu, const vec3& ev, std::shared_ptr<material> m) : Q(q), u(eu), v(ev), mat(m) {
+    vec3 n = cross(u, v);
+    normal = unit_vector(n);
+    D = dot(normal, Q);
+    w = n / dot(n, n);
+    set_bounding_box();
+  }
+  virtual void set_bounding_box() {
+    aabb d1(Q, Q + u + v);
+    aabb d2(Q + u, Q + v);
+    bbox = aabb(d1, d2);
+  }
+  aabb bounding_box() const override { return bbox; }
+  virtual bool is_interior(double a, double b, hit_record& rec) const {
+    interval unit(0.0f, 1.0f);
+    if (!unit.contains(a) || !unit.contains(b)) return false;
+    rec.u = a, rec.v = b;
+    return true;
+  }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_QUAD, bbox);
+    b.hittables[id].prim_id = b.n_prims++;
+    for (int c = 0; c < 3; c++) {
+      b.hittables[id].p[c] = Q[c];
+      b.hittables[id].p[3 + c] = u[c];
+      b.hittables[id].p[6 + c] = v[c];
+    }
+    int32_t m = rtb200_flatten_material(b, mat.get());
+    b.hittables[id].material = m;
+    return id;
+  }
+
+ private:
+  point3 Q;
+  vec3 u, v, w;
+  std::shared_ptr<material> mat;
+  aabb bbox;
+  vec3 normal;
+  double D;
+};
+
+// quad.hpp:129-159 — six sides in the order +z, +x, -z, -x, +y, -y.
+inline std::shared_ptr<hittable_list> box(const point3& a, const point3& b, std::shared_ptr<material> mat) {
+  auto sides = std::make_shared<hittable_list>();
+  point3 lo(std::fmin(a.x(), b.x()), std::fmin(a.y(), b.y()), std::fmin(a.z(), b.z()));
+  point3 hi(std::fmax(a.x(), b.x()), std::fmax(a.y(), b.y()), std::fmax(a.z(), b.z()));
+  vec3 dx(hi.x() - lo.x(), 0.0f, 0.0f), dy(0.0f, hi.y() - lo.y(), 0.0f), dz(0.0f, 0.0f, hi.z() - lo.z());
+  sides->add(std::make_shared<quad>(point3(lo.x(), lo.y(), hi.z()), dx, dy, mat));
+  sides->add(std::make_shared<quad>(point3(hi.x(), lo.y(), hi.z()), -dz, dy, mat));
+  sides->add(std::make_shared<quad>(point3(hi.x(), lo.y(), lo.z()), -dx, dy, mat));
+  sides->add(std::make_shared<quad>(point3(lo.x(), lo.y(), lo.z()), dz, dy, mat));
+  sides->add(std::make_shared<quad>(point3(lo.x(), hi.y(), hi.z()), dx, -dz, mat));
+  sides->add(std::make_shared<quad>(point3(lo.x(), lo.y(), lo.z()), dx, dz, mat));
+  return sides;
+}
+
+// Not in the reference: "The Next Week" constant_medium.
+class constant_medium : public hittable {
+ public:
+  constant_medium(std::shared_ptr<hittable> b, double density, std::shared_ptr<texture> tex)
+      : boundary(b), dens(density), neg_inv_density(-1 / density), phase_function(std::make_shared<isotropic>(tex)) {}
+  constant_medium(std::shared_ptr<hittable> b, double density, const color& albedo)
+      : boundary(b), dens(density), neg_inv_density(-1 / density), phase_function(std::make_shared<isotropic>(albedo)) {}
+  aabb bounding_box() const override { return boundary->bounding_box(); }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_MEDIUM, boundary->bounding_box());
+    b.hittables[id].p[0] = dens;
+    b.hittables[id].p[1] = neg_inv_density;
+    int32_t child = rtb200_flatten_hittable(b, boundary.get());
+    b.hittables[id].child0 = child;
+    int32_t m = rtb200_flatten_material(b, phase_function.get());
+    b.hittables[id].material = m;
+    return id;
+  }
+
+ private:
+  std::shared_ptr<hittable> boundary;
+  double dens, neg_inv_density;
+  std::shared_ptr<material> phase_function;
+};
+
+// accelerator/bvh_node.hpp:16-134.  The topology is kept (the CPU oracle replays the
+// reference's left-then-right traversal over it); the GPU builds its own SAH tree over
+// the leaves.  Same split rule and the same std::sort call as the reference, so the same
+// libstdc++ produces the same tree.
+class bvh_node : public hittable {
+ public:
+  bvh_node(hittable_list list) : bvh_node(list.objects, 0, list.objects.size()) {}
+  bvh_node(std::vector<std::shared_ptr<hittable>>& objects, size_t start, size_t end) {
+    bbox = aabb::empty;
+    for (size_t i = start; i < end; i++) bbox = aabb(bbox, objects[i]->bounding_box());
+    const int axis = bbox.longest_axis();
+    const size_t span = end - start;
+    if (span == 1) {
+      left = right = objects[start];
+    } else if (span == 2) {
+      left = objects[start];
+      right = objects[start + 1];
+    } else {
+      std::sort(std::begin(objects) + start, std::begin(objects) + end,
+                axis == 0 ? before<0> : (axis == 1 ? before<1> : before<2>));
+      size_t mid = start + span / 2;
+      left = std::make_shared<bvh_node>(objects, start, mid);
+      right = std::make_shared<bvh_node>(objects, mid, end);
+    }
+  }
+  aabb bounding_box() const override { return bbox; }
+  int32_t flatten(rtb200::scene_builder& b) const override {
+    int32_t id = b.new_hittable(this, RT_H_BVH, bbox);
+    int32_t l = rtb200_flatten_hittable(b, left.get());
+    int32_t r = rtb200_flatten_hittable(b, right.get());
+    b.hittables[id].child0 = l;
+    b.hittables[id].child1 = r;
+    return id;
+  }
+
+ private:
+  template <int AXIS>
+  static bool before(const std::shared_ptr<hittable> a, const std::shared_ptr<hittable> b) {
+    return a->bounding_box().axis_interval(AXIS).min < b->bounding_box().axis_interval(AXIS).min;
+  }
+  std::shared_ptr<hittable> left, right;
+  aabb bbox;
+};
+
+// ---------------------------------------------------------------------------------------
+namespace rtb200 {
+
+// Flatten a world into an owning scene_builder (desc() gives the C-ABI view).
+inline std::unique_ptr<scene_builder> flatten_world(const hittable& world) {
+  std::unique_ptr<scene_builder> b(new scene_builder);
+  b->root = rtb200_flatten_hittable(*b, &world);
+  for (size_t i = 0; i < b->images.size(); i++)
+    b->images[i].rgb = b->image_storage[i].empty() ? nullptr : b->image_storage[i].data();
+  return b;
+}
+
+}  // namespace rtb200
+
+// ---------------------------------------------------------------------------------------
+// core/camera.hpp:10-245 — same public fields, same render(std::ostream&, world) signature,
+// same PPM text (header :36-37, one "r g b\n" per pixel, color.hpp:57) and the same stdout
+// progress strings (:47,:70).  The pixel/sample/bounce loops run on the GPU.
+class camera {
+ public:
+  double aspect_ratio = 1.0f;
+  int image_width = 100;
+  int samples_per_pixel = 10;
+  int max_depth = 10;
+  color background;
+  double vfov = 90.0f;
+  point3 lookfrom = point3(0.0f, 0.0f, 0.0f);
+  point3 lookat = point3(0.0f, 0.0f, -1.0f);
+  vec3 vup = vec3(0.0f, 1.0f, 0.0f);
+  double defocus_angle = 0.0f;
+  double focus_dist = 10.0f;
+
+  rt_camera_desc desc() const {
+    rt_camera_desc c;
+    std::memset(&c, 0, sizeof c);
+    c.aspect_ratio = aspect_ratio;
+    c.image_width = image_width;
+    c.samples_per_pixel = samples_per_pixel;
+    c.max_depth = max_depth;
+    c.vfov = vfov;
+    c.defocus_angle = defocus_angle;
+    c.focus_dist = focus_dist;
+    for (int i = 0; i < 3; i++) {
+      c.background[i] = background[i];
+      c.lookfrom[i] = lookfrom[i];
+      c.lookat[i] = lookat[i];
+      c.vup[i] = vup[i];
+    }
+    return c;
+  }
+
+  void render(std::ostream& output_stream, const hittable& world);
+};
+
+#ifndef RTB200_NO_RENDER_IMPL
+namespace rtb200 {
+inline void die(rt_ctx* ctx, const char* where, int rc) {
+  std::fprintf(stderr, "rtb200: %s failed (%d): %s\n", where, rc, rt_last_error(ctx));
+  std::exit(1);
+}
+// Fast integer formatting of the P3 body: at GPU speed the iostream << of W*H lines is a
+// visible share of wall time.
+inline void write_ppm_p3(std::ostream& out, int w, int h, const uint8_t* rgb) {
+  out << "P3\n" << w << ' ' << h << "\n255\n";
+  std::string buf;
+  buf.reserve(size_t(w) * 12 * 64);
+  char num[256][4];
+  int len[256];
+  for (int v = 0; v < 256; v++) len[v] = std::snprintf(num[v], 4, "%d", v);
+  for (int j = 0; j < h; j++) {
+    for (int i = 0; i < w; i++) {
+      const uint8_t* p = rgb + (size_t(j) * w + i) * 3;
+      buf.append(num[p[0]], len[p[0]]);
+      buf.push_back(' ');
+      buf.append(num[p[1]], len[p[1]]);
+      buf.push_back(' ');
+      buf.append(num[p[2]], len[p[2]]);
+      buf.push_back('\n');
+    }
+    if (buf.size() > (1u << 20)) {
+      out.write(buf.data(), std::streamsize(buf.size()));
+      buf.clear();
+    }
+  }
+  out.write(buf.data(), std::streamsize(buf.size()));
+}
+}  // namespace rtb200
+
+inline void camera::render(std::ostream& output_stream, const hittable& world) {
+  rt_camera_desc cam = desc();
+  rt_camera_frame frame;
+  rt_camera_initialize(&cam, &frame);
+  std::printf("\rScanlines remaining: %d ", frame.image_height);
+  std::fflush(stdout);
+
+  auto scene = rtb200::flatten_world(world);
+  rt_scene_desc sd = scene->desc();
+
+  // RT_B200_DEVICES = comma-separated CUDA ordinals (default "0"); samples are sharded
+  // over them and the int64 accumulators are summed on the first one.
+  std::vector<int> devices;
+  const char* env = std::getenv("RT_B200_DEVICES");
+  std::string spec = env ? env : "0";
+  for (size_t pos = 0; pos < spec.size();) {
+    size_t comma = spec.find(',', pos);
+    if (comma == std::string::npos) comma = spec.size();
+    if (comma > pos) devices.push_back(std::atoi(spec.substr(pos, comma - pos).c_str()));
+    pos = comma + 1;
+  }
+  if (devices.empty()) devices.push_back(0);
+  if (int(devices.size()) > samples_per_pixel) devices.resize(size_t(std::max(1, samples_per_pixel)));
+
+  const int R = int(devices.size());
+  std::vector<rt_ctx*> ctx(size_t(R), nullptr);
+  for (int r = 0; r < R; r++) {
+    int rc = rt_init(devices[size_t(r)], &ctx[size_t(r)]);
+    if (rc != RT_OK) rtb200::die(nullptr, "rt_init", rc);
+    rc = rt_upload_scene(ctx[size_t(r)], &sd);
+    if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rc);
+  }
+  for (int r = 0; r < R; r++) {  // asynchronous: all devices render concurrently
+    rt_render_opts o;
+    std::memset(&o, 0, sizeof o);
+    o.seed = 0;
+    o.sample_begin = int32_t((int64_t(samples_per_pixel) * r) / R);
+    o.sample_count = int32_t((int64_t(samples_per_pixel) * (r + 1)) / R) - o.sample_begin;
+    o.clear = 1;
+    int rc = rt_render(ctx[size_t(r)], &cam, &o);
+    if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_render", rc);
+  }
+  const size_t npix = size_t(frame.image_width) * frame.image_height;
+  std::vector<uint8_t> rgb(npix * 3);
+  if (R == 1) {
+    int rc = rt_download(ctx[0], RT_BUF_RGB8, samples_per_pixel, rgb.data(), rgb.size());
+    if (rc != RT_OK) rtb200::die(ctx[0], "rt_download", rc);
+  } else {
+    // exact integer reduction on the host side of the boundary (order-independent)
+    std::vector<int64_t> total(npix * 3, 0), part(npix * 3);
+    for (int r = 0; r < R; r++) {
+      int rc = rt_download(ctx[size_t(r)], RT_BUF_ACCUM_I64, samples_per_pixel, part.data(), part.size() * 8);
+      if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_download", rc);
+      for (size_t i = 0; i < total.size(); i++) total[i] += part[i];
+    }
+    const double scale = (1.0f / samples_per_pixel) / 4294967296.0;
+    const float hi = 0.999f;
+    for (size_t i = 0; i < total.size(); i++) {
+      float lin = float(double(total[i]) * scale);
+      float g = lin > 0.0f ? std::sqrt(lin) : 0.0f;
+      g = g < 0.0f ? 0.0f : (g > hi ? hi : g);
+      rgb[i] = uint8_t(int(256 * g));
+    }
+  }
+  for (int r = 0; r < R; r++) rt_shutdown(ctx[size_t(r)]);
+
+  rtb200::write_ppm_p3(output_stream, frame.image_width, frame.image_height, rgb.data());
+  std::printf("\rDone.                       \n");
+  std::fflush(stdout);
+}
+#endif  // RTB200_NO_RENDER_IMPL
+
+#endif  // RTB200_HOST_HPP
