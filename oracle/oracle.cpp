@@ -64,16 +64,34 @@ struct Ray {
 // generator through random_r with a private state, i.e. srand(seed) per thread.
 struct Rng {
   bool global = true;
+  bool xoshiro = false;  // diagnostic mode: a high-quality generator instead of glibc's
+                         // lagged-Fibonacci rand() (which has 3-point correlations), to tell
+                         // "reference RNG artefact" from "algorithm" in statistical comparisons
   struct random_data rd;
   char state[128];
+  uint64_t xs[4];
   void seed_private(unsigned s) {
     global = false;
     std::memset(&rd, 0, sizeof rd);
     std::memset(state, 0, sizeof state);
     initstate_r(s, state, sizeof state, &rd);
+    uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t(s) + 1);
+    for (int i = 0; i < 4; i++) {  // splitmix64
+      z += 0x9E3779B97F4A7C15ull;
+      uint64_t x = z;
+      x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+      x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+      xs[i] = x ^ (x >> 31);
+    }
   }
   int next() {
     if (global) return std::rand();
+    if (xoshiro) {  // xoshiro256**, top 31 bits
+      auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
+      uint64_t r = rotl(xs[1] * 5, 7) * 9, t = xs[1] << 17;
+      xs[2] ^= xs[0], xs[3] ^= xs[1], xs[1] ^= xs[2], xs[0] ^= xs[3], xs[2] ^= t, xs[3] = rotl(xs[3], 45);
+      return int(r >> 33);
+    }
     int32_t v;
     random_r(&rd, &v);
     return v;
@@ -572,7 +590,8 @@ int orc_render_linear(const rt_scene_desc* d, const rt_camera_desc* cam, int spp
   std::vector<uint64_t> rays(size_t(threads), 0);
   auto work = [&](int tid) {
     Rng rng;
-    rng.seed_private(seed * 4099u + unsigned(tid));
+    rng.seed_private((seed & 0x7FFFFFFFu) * 4099u + unsigned(tid));
+    rng.xoshiro = (seed & 0x80000000u) != 0;  // top bit of the seed selects the diagnostic generator
     uint64_t nr = 0;
     for (int j = tid; j < k.H; j += threads)
       for (int i = 0; i < k.W; i++) {

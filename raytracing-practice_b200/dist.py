@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), samples sharded by index, exact int64
+reduce to rank 0.  torch.distributed is plumbing only — the data path is the CUDA library.
+
+The path shards naturally: every (pixel, sample) path is independent; the only
+exchange step is the per-pixel sum (camera.hpp:55-65).  Each rank renders sample indices
+[begin, begin+count) of EVERY pixel into its own fixed-point int64 accumulator; because the
+Philox stream is keyed on (pixel, sample, bounce) and integer addition is associative, the reduced
+image is bit-identical for any world size.
+"""
+import os
+
+
+def shard_samples(spp, rank, world):
+    """Contiguous, exhaustive, non-overlapping split of sample indices 0..spp-1 (sizes differ by <= 1)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    begin = (spp * rank) // world
+    end = (spp * (rank + 1)) // world
+    return begin, end - begin
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init_process_group(backend=None):
+    """Rendezvous from the torchrun environment (127.0.0.1 by default)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def reduce_accum_to_rank0(accum_tensor):
+    """Exact sum of the per-rank int64 accumulators onto rank 0 (NCCL over NVLink on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return accum_tensor
+    assert accum_tensor.dtype == torch.int64
+    dist.reduce(accum_tensor, dst=0, op=dist.ReduceOp.SUM)
+    return accum_tensor
+
+
+def render_sharded(ctx, cam, seed=0):
+    """rt_render of this rank's sample shard, then the reduce.  Rank 0's accumulator holds the image."""
+    import torch
+
+    rank, _, world = env_rank()
+    begin, count = shard_samples(cam.samples_per_pixel, rank, world)
+    if count > 0:
+        ctx.render(cam, seed=seed, sample_begin=begin, sample_count=count, clear=True)
+    ctx.synchronize()
+    if world > 1:
+        reduce_accum_to_rank0(ctx.accum_tensor())
+        torch.cuda.synchronize()

@@ -1,0 +1,200 @@
+"""T4/T5/T6 — the rendered image: converged-image parity against the CPU oracle (RNG streams
+differ, so parity is statistical with a variance-derived tolerance), sharding invariance
+(bit-exact), determinism, the write_color tail and the C-ABI's error behaviour."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scene_util as su
+from conftest import ALL_SCENES
+
+pytestmark = pytest.mark.gpu
+
+GPU_SPP, CPU_SPP = 4096, 256
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_converged_image_matches_oracle(rtb, orc, gpu_ctx, name):
+    """Gate 1 (north_star): per-channel RMSE after write_color's gamma <= tolerance, where the
+    tolerance is 1.3 x the RMSE the two estimators' own Monte-Carlo noise predicts.
+    Gate 2 (bias): channel means within 5 standard errors.  Oracle = the reference algorithm
+    in fp64 driven by a good generator (see orc.render_linear about glibc rand())."""
+    sc = rtb.Scene(name, rand_seed=1)
+    width = 96 if sc.cam.contents.aspect_ratio > 1.2 else 72
+    cam = sc.camera_copy(image_width=width, samples_per_pixel=GPU_SPP)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=17)
+    img = gpu_ctx.download_radiance(GPU_SPP).astype(np.float64)
+    st = gpu_ctx.stats()
+    mean, var, orays = orc.render_linear(sc.desc, cam, spp=CPU_SPP, seed=23)
+    var_tot = var * (1.0 + CPU_SPP / GPU_SPP)
+    # gate 2: bias
+    for c in range(3):
+        z = (img[..., c].sum() - mean[..., c].sum()) / np.sqrt(var_tot[..., c].sum() + 1e-30)
+        assert abs(z) < 5.0, f"channel {c}: z = {z:.2f}"
+    # gate 1: RMSE after gamma, tolerance propagated through d sqrt(x)/dx = 1 / (2 sqrt(x))
+    g_gpu = np.sqrt(np.clip(img, 0, 0.999 ** 2))
+    g_cpu = np.sqrt(np.clip(mean, 0, 0.999 ** 2))
+    rmse = np.sqrt(np.mean((g_gpu - g_cpu) ** 2, axis=(0, 1)))
+    lin = np.maximum(0.5 * (img + mean), 1e-4)
+    predicted = np.sqrt(np.mean(var_tot / (4.0 * lin), axis=(0, 1)))
+    assert np.all(rmse <= 1.3 * predicted + 2e-3), (rmse, predicted)
+    # same path-length statistics (rays per sample)
+    rps_gpu, rps_cpu = st.rays / st.samples, orays / (mean.shape[0] * mean.shape[1] * CPU_SPP)
+    assert abs(rps_gpu - rps_cpu) / rps_cpu < 0.01
+    assert st.samples == mean.shape[0] * mean.shape[1] * GPU_SPP
+
+
+def test_image_is_independent_of_sample_sharding(rtb, gpu_ctx):
+    """T5: Philox keyed on (pixel, sample, bounce) + int64 fixed-point sums => the accumulator is
+    BIT-identical whether 64 spp are rendered in one launch, in 4 launches of 16, or as 8
+    uneven 'rank' shards — i.e. independent of GPU count."""
+    sc = rtb.Scene("cornell_smoke", rand_seed=1)
+    cam = sc.camera_copy(image_width=80, samples_per_pixel=64, max_depth=12)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=3)
+    whole = gpu_ctx.download_accum()
+    for shards in ([16, 16, 16, 16], [1, 7, 8, 13, 3, 20, 5, 7]):
+        begin = 0
+        for i, n in enumerate(shards):
+            gpu_ctx.render(cam, seed=3, sample_begin=begin, sample_count=n, clear=(i == 0))
+            begin += n
+        assert begin == 64
+        assert np.array_equal(gpu_ctx.download_accum(), whole)
+    gpu_ctx.render(cam, seed=4)
+    assert not np.array_equal(gpu_ctx.download_accum(), whole)  # the seed matters
+    gpu_ctx.render(cam, seed=3)
+    assert np.array_equal(gpu_ctx.download_accum(), whole)  # and the render is deterministic
+
+
+def test_peer_accumulation_two_contexts(rtb, gpu_ctx):
+    """Two contexts ('ranks') render disjoint sample shards; rank 1 adds straight into rank 0's
+    accumulator (rt_render_opts.peer_accum, the fused reduce).  Same bits as one context."""
+    sc = rtb.Scene("simple_light", rand_seed=1)
+    cam = sc.camera_copy(image_width=96, samples_per_pixel=48)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=8)
+    whole = gpu_ctx.download_accum()
+    other = rtb.Context(0)
+    other.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=8, sample_begin=0, sample_count=20)
+    gpu_ctx.synchronize()
+    ptr, nbytes = gpu_ctx.accum_ptr()
+    assert nbytes == whole.nbytes
+    other.render(cam, seed=8, sample_begin=20, sample_count=28, peer_accum=ptr)
+    other.synchronize()
+    assert np.array_equal(gpu_ctx.download_accum(), whole)
+    other.close()
+
+
+def test_write_color_tail_and_ppm(rtb, orc, gpu_ctx, tmp_path):
+    """RT_BUF_RGB8 is write_color (color.hpp:26-58) applied to the radiance; P3 text format."""
+    sc = rtb.Scene("quads", rand_seed=1)
+    cam = sc.camera_copy(image_width=50, samples_per_pixel=30)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=1)
+    acc = gpu_ctx.download_accum()
+    rgb = gpu_ctx.download_rgb8(30)
+    lin = acc.astype(np.float64) / 2.0 ** 32 * np.float64(np.float32(1.0) / np.float32(30))
+    assert np.array_equal(rgb, orc.write_color(lin))
+    rad = gpu_ctx.download_radiance(30)
+    assert np.allclose(rad, lin, rtol=1e-6)
+    path = tmp_path / "o.ppm"
+    rtb.write_ppm_p3(str(path), rgb)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "P3" and lines[1] == "50 50" and lines[2] == "255" and len(lines) == 3 + 2500 + 1
+    assert all(0 <= int(x) <= 255 for x in lines[3].split())
+
+
+def test_background_only_and_zero_depth(rtb, gpu_ctx):
+    s = su.SceneDesc()
+    desc = s.finish(s.list([]))
+    gpu_ctx.upload_scene(desc)
+    cam = su.camera(width=33, aspect=16 / 9, spp=5, depth=10, bg=(0.25, 0.5, 1.0))
+    gpu_ctx.render(cam)
+    acc = gpu_ctx.download_accum()
+    assert acc.shape == (18, 33, 3)
+    assert np.all(acc == (np.array([0.25, 0.5, 1.0]) * 5 * 2 ** 32).astype(np.int64))
+    st = gpu_ctx.stats()
+    assert st.rays == 33 * 18 * 5 and st.samples == 33 * 18 * 5
+    cam.max_depth = 0  # ray_color returns black immediately (camera.hpp:183-186)
+    gpu_ctx.render(cam)
+    assert not gpu_ctx.download_accum().any()
+    assert gpu_ctx.stats().rays == 0
+
+
+def test_full_size_headline_scene_properties(rtb, gpu_ctx):
+    """BASELINE config 5 at its full 800x800 size (reduced spp): shard additivity (a checksum of
+    checksums) and sample accounting — size-independent properties, the oracle is too slow here."""
+    sc = rtb.Scene("book2_final", rand_seed=1)
+    cam = sc.camera_copy(samples_per_pixel=32)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=0)
+    whole = gpu_ctx.download_accum()
+    st = gpu_ctx.stats()
+    assert whole.shape == (800, 800, 3) and st.samples == 800 * 800 * 32
+    assert 3.5 < st.rays / st.samples < 6.5
+    total = np.zeros_like(whole)
+    for r in range(8):  # 8 'ranks', each in its own cleared accumulator, summed on the host
+        gpu_ctx.render(cam, seed=0, sample_begin=4 * r, sample_count=4, clear=True)
+        total += gpu_ctx.download_accum()
+    assert np.array_equal(total, whole)
+    assert whole.min() >= 0
+
+
+def test_error_behaviour(rtb, built):
+    lib = rtb.cuda_lib()
+    ctx = rtb.Context(0)
+    cam = su.camera()
+    with pytest.raises(rtb.RtError, match="rt_upload_scene"):
+        ctx.render(cam)
+    s = su.SceneDesc()
+    k = s.sphere((0, 0, 0), 1, s.lambertian(s.solid(1, 1, 1)))
+    s.h[k].kind = 99  # a hittable subclass the flattener does not know
+    desc = s.finish(k)
+    assert lib.rt_upload_scene(ctx._h, desc) == rtb.RT_ERR_UNSUPPORTED
+    assert b"unknown hittable" in lib.rt_last_error(ctx._h)
+    s = su.SceneDesc()
+    desc = s.finish(s.sphere((0, 0, 0), 1, 5))  # material index out of range
+    assert lib.rt_upload_scene(ctx._h, desc) == rtb.RT_ERR_INVALID
+    s = su.SceneDesc()
+    desc = s.finish(s.sphere((0, 0, 0), 1, s.lambertian(s.solid(1, 1, 1))))
+    ctx.upload_scene(desc)
+    bad = su.camera(width=0)
+    with pytest.raises(rtb.RtError):
+        ctx.render(bad)
+    buf = np.zeros(4, np.uint8)
+    ctx.render(su.camera(width=8, spp=1))
+    assert lib.rt_download(ctx._h, rtb.RT_BUF_RGB8, 1, buf.ctypes.data_as(C.c_void_p), buf.nbytes) == rtb.RT_ERR_INVALID
+    ctx.close()
+
+
+def test_cpp_drop_in_camera_render(rtb, gpu_ctx, tmp_path):
+    """The C++ host path a reference user takes: scene classes -> camera::render(ostream, world)
+    -> flatten -> rt_upload_scene / rt_render / rt_download -> P3 text.  Must equal the image
+    the Python binding produces from the same scene (same seed, same kernel)."""
+    import os
+    import subprocess
+
+    host = os.path.join(rtb.REPO_ROOT, "raytracing-practice_b200", "host")
+    exe = str(tmp_path / "dropin")
+    libdir = os.path.dirname(rtb.CUDA_LIB_PATH)
+    cmd = ["g++", "-std=c++11", "-O1", "-I", host, "-I", os.path.join(rtb.REPO_ROOT, "include"),
+           os.path.join(rtb.REPO_ROOT, "tests", "cpp", "dropin_main.cpp"), "-L", libdir, "-lrt_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for devices in ("0", "0,0,0"):  # one context, then three 'ranks' on the same device summed on the host
+        out = str(tmp_path / f"img_{len(devices)}.ppm")
+        env = dict(os.environ, RT_B200_DEVICES=devices)
+        r = subprocess.run([exe, "cornell_rotated", out, "90", "40"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "Scanlines remaining" in r.stdout and "Done." in r.stdout  # camera.hpp:47,70
+        tok = open(out).read().split()
+        assert tok[:4] == ["P3", "90", "90", "255"]
+        img = np.array(tok[4:], dtype=np.int64).reshape(90, 90, 3)
+        sc = rtb.Scene("cornell_rotated", rand_seed=1)
+        cam = sc.camera_copy(image_width=90, samples_per_pixel=40)
+        gpu_ctx.upload_scene(sc.desc)
+        gpu_ctx.render(cam, seed=0)
+        assert np.array_equal(img, gpu_ctx.download_rgb8(40).astype(np.int64))

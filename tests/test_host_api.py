@@ -1,0 +1,127 @@
+"""Host side of the boundary (no GPU): the C++ mirror of the reference's scene API, the
+flattener, the JPEG decoder, and the scene converter inside the C-ABI library."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ALL_SCENES
+
+REF = "/root/reference"
+
+
+def test_all_named_scenes_flatten(rtb, built, pins):
+    assert set(rtb.scene_names()) == set(ALL_SCENES)
+    for name in ALL_SCENES:
+        sc = rtb.Scene(name, rand_seed=1)
+        d = sc.desc.contents
+        assert d.abi_version == rtb.RT_B200_ABI_VERSION and 0 <= d.root < d.n_hittables
+        assert d.n_prims == pins["scenes"][name]["primary_full"]["prims"]
+        kinds = [d.hittables[i].kind for i in range(d.n_hittables)]
+        ids = sorted(d.hittables[i].prim_id for i in range(d.n_hittables) if kinds[i] in (rtb.RT_H_SPHERE, rtb.RT_H_QUAD))
+        assert ids == list(range(d.n_prims))  # dense DFS numbering, shared leaves once
+    d = rtb.Scene("book2_final", rand_seed=1).desc.contents
+    kinds = [d.hittables[i].kind for i in range(d.n_hittables)]
+    assert kinds.count(rtb.RT_H_MEDIUM) == 2 and kinds.count(rtb.RT_H_ROTATE_Y) == 1 and kinds.count(rtb.RT_H_TRANSLATE) == 1
+    assert kinds.count(rtb.RT_H_QUAD) == 2401 and kinds.count(rtb.RT_H_SPHERE) == 1007
+    assert d.n_perlins == 1 and d.n_images == 1
+
+
+def test_scene_construction_follows_the_rand_stream(rtb, built):
+    """rand() consumption: same seed -> identical bytes; the unseeded default is srand(1)."""
+    a = rtb.Scene("bouncing_spheres", rand_seed=1)
+    b = rtb.Scene("bouncing_spheres", rand_seed=1)
+    c = rtb.Scene("bouncing_spheres", rand_seed=2)
+    n = a.desc.contents.n_hittables
+    raw = lambda s: C.string_at(s.desc.contents.hittables, n * C.sizeof(rtb.rt_hittable))  # noqa: E731
+    assert raw(a) == raw(b) and a.desc.contents.n_hittables == b.desc.contents.n_hittables
+    assert c.desc.contents.n_hittables != n or raw(c) != raw(a)
+
+
+def test_jpeg_decoder_matches_libjpeg_bit_for_bit(rtb, built, pins):
+    d = rtb.default_image_dir()
+    if d is None:
+        pytest.skip("earthmap.jpg is not available on this machine")
+    lib = rtb.scenes_lib()
+    p, w, h = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int()
+    path = os.path.join(d, "earthmap.jpg").encode()
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == pins["earthmap"]["jpeg_sha256"]
+    assert lib.rth_load_texture(path, 0, C.byref(p), C.byref(w), C.byref(h)) == 0
+    assert (w.value, h.value) == (pins["earthmap"]["width"], pins["earthmap"]["height"])
+    raw = C.string_at(p, w.value * h.value * 3)
+    lib.rth_free(p)
+    assert hashlib.sha256(raw).hexdigest() == pins["earthmap"]["rgb8_sha256"]  # == PIL / libjpeg-turbo
+    # rtw_image conventions on top: stb's gamma-2.2 linearisation then float_to_byte
+    assert lib.rth_load_texture(path, 1, C.byref(p), C.byref(w), C.byref(h)) == 0
+    lin = np.frombuffer(C.string_at(p, w.value * h.value * 3), np.uint8)
+    lib.rth_free(p)
+    src = np.frombuffer(raw, np.uint8)
+    lut = {64: 12, 128: 56, 200: 150, 254: 253, 255: 255, 0: 0}
+    for k, v in lut.items():
+        if (src == k).any():
+            assert np.all(lin[src == k] == v)
+    assert lib.rth_load_texture(b"/nonexistent/x.jpg", 0, C.byref(p), C.byref(w), C.byref(h)) != 0
+
+
+def test_jpeg_decoder_subsampled_and_restart_files(rtb, built, tmp_path):
+    """4:2:2 / 4:2:0 / grayscale / restart-interval files, encoded here with PIL, decoded by both."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    base = (rng.random((61, 83, 3)) * 255).astype(np.uint8)
+    base = np.asarray(Image.fromarray(base).resize((83 * 2, 61 * 2), Image.BICUBIC))
+    lib = rtb.scenes_lib()
+    for tag, kw, mode in [("444", dict(subsampling=0), "RGB"), ("422", dict(subsampling=1), "RGB"), ("420", dict(subsampling=2), "RGB"),
+                          ("gray", {}, "L"), ("rst", dict(subsampling=2, restart_marker_blocks=3), "RGB")]:
+        path = str(tmp_path / f"{tag}.jpg")
+        Image.fromarray(base).convert(mode).save(path, quality=88, **kw)
+        want = np.asarray(Image.open(path).convert("RGB"))
+        p, w, h = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int()
+        assert lib.rth_load_texture(path.encode(), 0, C.byref(p), C.byref(w), C.byref(h)) == 0, tag
+        got = np.frombuffer(C.string_at(p, w.value * h.value * 3), np.uint8).reshape(h.value, w.value, 3)
+        lib.rth_free(p)
+        assert np.array_equal(got, want), tag
+
+
+def test_scene_converter_counts_and_errors(rtb, built):
+    lib = C.CDLL(rtb.CUDA_LIB_PATH)
+    lib.rt_debug_build_stats.argtypes = [C.POINTER(rtb.rt_scene_desc), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    want = {"bouncing_spheres": (484, 0, 0), "cornell_box": (0, 18, 0), "cornell_smoke": (0, 18, 2), "book2_final": (1008, 2401, 2)}
+    for name, (ns, nq, nm) in want.items():
+        sc = rtb.Scene(name, rand_seed=1)
+        cnt = (C.c_int32 * 8)()
+        assert lib.rt_debug_build_stats(sc.desc, cnt, None) == 0
+        assert (cnt[1], cnt[2], cnt[3]) == (ns, nq, nm), name
+        assert 1 <= cnt[0] <= max(1, ns + nq) and cnt[5] <= 32  # nodes, depth within the traversal stack
+    import scene_util as su
+
+    s = su.SceneDesc()
+    k = s.sphere((0, 0, 0), 1, s.lambertian(s.solid(1, 1, 1)))
+    s.h[k].kind = 42
+    assert lib.rt_debug_build_stats(s.finish(k), None, None) != 0
+    s = su.SceneDesc()
+    bad = s.finish(s.list([]))
+    s.desc.root = 99
+    assert lib.rt_debug_build_stats(bad, None, None) != 0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_main_cpp_compiles_unchanged_against_the_host_api(rtb, tmp_path):
+    """Drop-in: the reference's own src/main.cpp (all seven scene functions + main) compiles against
+    raytracing-practice_b200/host with no source change and links against the C-ABI library."""
+    host = os.path.join(rtb.REPO_ROOT, "raytracing-practice_b200", "host")
+    exe = str(tmp_path / "raytracer")
+    # main.cpp is fed through stdin so that its quoted includes ("common/rtweekend.hpp", ...) resolve
+    # through -I (our host API) instead of the reference's own directory; the text is untouched.
+    cmd = ["g++", "-std=c++11", "-O1", "-x", "c++", "-", "-I", host, "-I", os.path.join(rtb.REPO_ROOT, "include"),
+           "-L", os.path.dirname(rtb.CUDA_LIB_PATH), "-lrt_b200", "-Wl,-rpath," + os.path.dirname(rtb.CUDA_LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), input=open(os.path.join(REF, "src", "main.cpp"), encoding="utf-8").read())
+    assert r.returncode == 0, r.stderr[-3000:]
+    # without a GPU the binary must fail loudly (no CPU fallback), not render something else
+    import torch
+
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe, str(tmp_path / "image.ppm")], capture_output=True, text=True, cwd=str(tmp_path))
+        assert out.returncode != 0 and "rt_init" in out.stderr
