@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — the hot path (camera::render's pixel x sample loop) on BASELINE.json's headline
+configuration: Book-2 final scene, 800x800, 10,000 spp, max_depth 40 (config C5).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
+
+One STEP = one full render of the workload: every rank renders its shard of the sample indices
+of every pixel (strong scaling: the job is fixed, N ranks split the 10,000 spp), then the exact
+int64 reduce to rank 0.  `value` = W*H*spp / (max-over-ranks device time per step), scene resident
+in HBM.  `e2e` = the same job through the C-ABI with HOST buffers: rt_upload_scene (H2D of the
+flattened scene) + rt_render + reduce + rt_download of the RGB8 image (D2H), wall clock.
+The oracle / reference harness is executed ONLY by the cpu_baseline and --impl reference legs.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENE = "book2_final"
+METRIC = "samples_px_per_s"
+UNIT = "samples*px/s"
+# flop-equivalents per unit of algorithmic work (one slab test = 12 flop + 12 cmp/sel)
+F_BOX, F_SPH_MISS, F_SPH_HIT, F_QUAD_EARLY, F_QUAD_FULL, F_MEDIUM = 24, 29, 60, 12, 54, 120
+F_SHADE = dict(lambertian=15, metal=35, dielectric=60, light=0, isotropic=15, checker=10, image=6, noise=1550, bounce=6)
+# bytes per unit (fp32 device layouts): BVH2 node with both child boxes 64 B, sphere 32 B, quad 48 B
+B_NODE, B_SPH, B_QUAD, B_TEXEL, B_PERLIN = 64, 32, 48, 4, 56 * 16 + 7 * 24
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default=SCENE)
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (0 = the config's 10,000)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--cpu-spp", type=int, default=3, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback", 1965.0
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_once(scene, width, spp, seed, native=False):
+    """One process of the UNMODIFIED reference (oracle/_ref/ref_harness): camera::render, serial."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness_native" if native else "ref_harness")
+    env = dict(os.environ)
+    rtb = importlib.import_module("raytracing-practice_b200")
+    if rtb.default_image_dir():
+        env["RTW_IMAGES"] = rtb.default_image_dir()
+    cmd = [exe, "ppm", scene, "/dev/null", "--spp", str(spp), "--seed", str(seed)] + (["--width", str(width)] if width else [])
+    return subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+
+def parse_harness(proc):
+    out, _ = proc.communicate()
+    line = [l for l in out.splitlines() if l.startswith("JSON ")]
+    if proc.returncode != 0 or not line:
+        raise RuntimeError("ref_harness failed")
+    return json.loads(line[-1][5:])
+
+
+def cpu_baseline(args):
+    """The reference's camera::render as shipped (1 process x 1 thread) on a bounded sample."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_harness")):
+        return oracle_port_baseline(args, threads=1)
+    j = parse_harness(cpu_reference_once(args.scene, args.width, args.cpu_spp, seed=1))
+    n = j["width"] * j["height"] * j["spp"]
+    return {"value": n / j["seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{args.scene} {j['width']}x{j['height']} at {j['spp']} spp (of the config's 10,000), max_depth {j['max_depth']}; "
+                      f"unmodified reference camera::render via oracle/_ref/ref_harness (g++ -O2), 1 process x 1 thread as shipped; "
+                      f"rotate_y/constant_medium/isotropic are oracle/ref_ext.hpp (absent from the reference)",
+            "seconds": j["seconds"], "rays": j["rays"], "mrays_per_s": j["rays"] / j["seconds"] / 1e6, "host_cores_available": os.cpu_count()}
+
+
+def oracle_port_baseline(args, threads):
+    rtb = importlib.import_module("raytracing-practice_b200")
+    from oracle import orc
+
+    sc = rtb.Scene(args.scene, rand_seed=1)
+    cam = sc.camera_copy(**({"image_width": args.width} if args.width else {}))
+    t0 = time.time()
+    _, _, rays = orc.render_linear(sc.desc, cam, spp=args.cpu_spp, seed=1, threads=threads, want_sq=False, rng="glibc")
+    dt = time.time() - t0
+    n = cam.image_width * rtb.image_height(cam) * args.cpu_spp
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{args.scene} {cam.image_width}x{rtb.image_height(cam)} at {args.cpu_spp} spp, oracle/oracle.cpp restatement", "seconds": dt,
+            "rays": rays, "mrays_per_s": rays / dt / 1e6, "host_cores_available": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on all host threads.  The reference
+    is serial and not re-entrant (global rand()), so 'all threads' = one process per core, each
+    rendering its own bounded sample with its own srand seed; throughput is aggregated."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rtb = importlib.import_module("raytracing-practice_b200")
+    cores = os.cpu_count() or 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_harness"))
+    spp_each = max(1, args.cpu_spp // 3)
+    times, last = [], None
+    for step in range(args.warmup + args.steps):
+        t0 = time.time()
+        if have_ref:
+            procs = [cpu_reference_once(args.scene, args.width, spp_each, seed=100 * step + c + 1) for c in range(cores)]
+            res = [parse_harness(p) for p in procs]
+            samples = sum(r["width"] * r["height"] * r["spp"] for r in res)
+            rays = sum(r["rays"] for r in res)
+            dims = (res[0]["width"], res[0]["height"], res[0]["max_depth"])
+        else:
+            from oracle import orc
+
+            sc = rtb.Scene(args.scene, rand_seed=1)
+            cam = sc.camera_copy(**({"image_width": args.width} if args.width else {}))
+            _, _, rays = orc.render_linear(sc.desc, cam, spp=spp_each * cores, seed=step + 1, threads=cores, want_sq=False, rng="glibc")
+            samples = cam.image_width * rtb.image_height(cam) * spp_each * cores
+            dims = (cam.image_width, rtb.image_height(cam), cam.max_depth)
+        dt = time.time() - t0
+        if step >= args.warmup:
+            times.append(dt)
+            last = (samples, rays)
+    sec = sum(times) / len(times)
+    value = last[0] / sec
+    sample = (f"{args.scene} {dims[0]}x{dims[1]}, max_depth {dims[2]}: {cores} processes x {spp_each} spp per step "
+              f"({'oracle/_ref/ref_harness = unmodified reference camera::render' if have_ref else 'oracle port'}), one per host core")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.scene} 800x800 x 10000 spp, max_depth 40 (BASELINE config 5); each CPU step is a bounded sample of it"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mrays_per_s": last[1] / sec / 1e6, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    rtb = importlib.import_module("raytracing-practice_b200")
+    dist = importlib.import_module("raytracing-practice_b200.dist")
+    rank, local_rank, world = dist.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    ctx = rtb.Context(local_rank)
+    sc = rtb.Scene(args.scene, rand_seed=1)
+    over = {}
+    if args.spp:
+        over["samples_per_pixel"] = args.spp
+    if args.width:
+        over["image_width"] = args.width
+    cam = sc.camera_copy(**over)
+    W, H, spp = cam.image_width, rtb.image_height(cam), cam.samples_per_pixel
+    begin, count = dist.shard_samples(spp, rank, world)
+    ctx.upload_scene(sc.desc)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def step(seed):
+        """Resident-scene step: this rank's shard + reduce; returns device ms (render + reduce)."""
+        flush.fill_(1)  # L2 flush between iterations (on torch's stream; finished before the render starts)
+        torch.cuda.synchronize()
+        ctx.render(cam, seed=seed, sample_begin=begin, sample_count=count, clear=True)
+        ms = ctx.stats().last_render_ms  # CUDA events recorded on the context's own stream
+        if world > 1:
+            acc = ctx.accum_tensor()
+            ev[0].record()
+            dist.reduce_accum_to_rank0(acc)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms += ev[0].elapsed_time(ev[1])
+        return ms
+
+    for i in range(args.warmup):
+        step(1000 + i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.stats().kernel_launches
+    t_wall0 = time.time()
+    dev_ms, rays = 0.0, 0
+    for i in range(args.steps):
+        dev_ms += step(i)
+        rays += ctx.stats().rays
+    barrier()
+    wall = time.time() - t_wall0
+    clocks = sampler.summary()
+    launches = ctx.stats().kernel_launches - launches0
+
+    # ---- e2e: the reference-facing C-ABI call sequence with host buffers ---------------------
+    e2e_steps = min(args.steps, 2)
+    scene_bytes = sum(getattr(sc.desc.contents, n) * C.sizeof(t) for n, t in
+                      [("n_hittables", rtb.rt_hittable), ("n_materials", rtb.rt_material), ("n_textures", rtb.rt_texture), ("n_perlins", rtb.rt_perlin)])
+    scene_bytes += 4 * sc.desc.contents.n_child_index
+    for k in range(sc.desc.contents.n_images):
+        scene_bytes += 3 * sc.desc.contents.images[k].width * sc.desc.contents.images[k].height
+    barrier()
+    t0 = time.time()
+    for i in range(e2e_steps):
+        ctx.upload_scene(sc.desc)  # host scene description -> device (H2D)
+        ctx.render(cam, seed=i, sample_begin=begin, sample_count=count, clear=True)
+        ctx.synchronize()
+        if world > 1:
+            dist.reduce_accum_to_rank0(ctx.accum_tensor())
+            torch.cuda.synchronize()
+        if rank == 0:
+            rgb = ctx.download_rgb8(spp)  # finished image -> host (D2H)
+    barrier()
+    e2e_sec = (time.time() - t0) / e2e_steps
+
+    # ---- census (instrumented kernel, untimed) for the roofline's algorithmic work -------------
+    census = None
+    if rank == 0:
+        c_spp = max(1, min(16, count))
+        ctx.render(cam, seed=0, sample_begin=begin, sample_count=c_spp, clear=True, flags=rtb.RT_RENDER_COUNTERS)
+        st = ctx.stats()
+        cs = list(st.census)
+        r = max(st.rays, 1)
+        keys = ["node", "sph", "sph_hit", "quad", "quad_full", "medium", "lambertian", "metal", "dielectric", "light", "isotropic", "checker", "image", "noise"]
+        per_ray = {k: cs[i] / r for i, k in enumerate(keys)}
+        flops = (2 * F_BOX * per_ray["node"] + F_SPH_MISS * (per_ray["sph"] - per_ray["sph_hit"]) + F_SPH_HIT * per_ray["sph_hit"]
+                 + F_QUAD_EARLY * (per_ray["quad"] - per_ray["quad_full"]) + F_QUAD_FULL * per_ray["quad_full"] + F_MEDIUM * per_ray["medium"]
+                 + sum(F_SHADE[k] * per_ray[k] for k in ("lambertian", "metal", "dielectric", "light", "isotropic", "checker", "image", "noise"))
+                 + F_SHADE["bounce"])
+        nbytes = (B_NODE * per_ray["node"] + B_SPH * per_ray["sph"] + B_QUAD * per_ray["quad"] + B_TEXEL * per_ray["image"] + B_PERLIN * per_ray["noise"])
+        census = dict(per_ray=per_ray, flops_per_ray=flops, bytes_per_ray=nbytes, rays_per_sample=st.rays / max(st.samples, 1))
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    vals = torch.tensor([dev_ms, wall * 1e3, e2e_sec * 1e3, float(rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        mx = vals.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        sm = vals.clone()
+        torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
+        dev_ms, wall_ms, e2e_ms, rays = mx[0].item(), mx[1].item(), mx[2].item(), sm[3].item()
+    else:
+        wall_ms, e2e_ms = wall * 1e3, e2e_sec * 1e3
+    if rank != 0:
+        ctx.close()
+        return 0
+
+    ms_per_step = dev_ms / args.steps
+    total_samples = W * H * spp
+    value = total_samples / (ms_per_step * 1e-3)
+    rays_per_step = rays / args.steps
+    mrays = rays_per_step / (ms_per_step * 1e-3) / 1e6
+    hbm_peak, which, sm_max = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
+    kernel_rays_s = rays_per_step / world / (ms_per_step * 1e-3)  # one launch = one rank's kernel
+    roofline = {"bound": "fp32-issue (not hbm, not tensor: the whole scene is L1/shared resident; SURVEY.md 8(d))",
+                "achieved": kernel_rays_s * census["flops_per_ray"] / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                "frac": kernel_rays_s * census["flops_per_ray"] / 1e12 / fp32_peak_tflops, "traffic": None,
+                "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal max clock)",
+                "flops_per_ray": census["flops_per_ray"], "bytes_per_ray": census["bytes_per_ray"], "census_per_ray": census["per_ray"],
+                "hbm": {"bound": "hbm", "achieved": kernel_rays_s * census["bytes_per_ray"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": kernel_rays_s * census["bytes_per_ray"] / 1e9 / hbm_peak, "peak_source": f"MEASURED_PEAKS.json ({which})",
+                        "note": "algorithmic node/primitive/texel bytes; they are served by shared memory and L1, not DRAM"}}
+    if clocks.get("sm_mhz"):
+        obs = sm_count * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12
+        roofline["frac_at_observed_clock"] = roofline["achieved"] / obs
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.scene} {W}x{H} x {spp} spp, max_depth {cam.max_depth} (BASELINE config 5: 400 ground boxes, 1000-sphere cluster, "
+                                   f"2 volumes, image + noise textures)", "sharding": f"sample index, {world} rank(s), exact int64 reduce to rank 0",
+                       "l2": "256 MB device write between timed steps (flush)", "seed": "Philox key = step index"},
+            "mrays_per_s": mrays, "rays_per_sample": rays_per_step / total_samples, "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": total_samples / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(W * H * 3),
+                    "steps": e2e_steps, "path": "rt_upload_scene + rt_render + reduce + rt_download(RGB8) with host buffers, wall clock"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args)
+            line["speedup_vs_cpu_baseline_1core"] = line["e2e"]["value"] / line["cpu_baseline"]["value"]
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

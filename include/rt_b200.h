@@ -205,7 +205,10 @@ typedef struct rt_render_opts {
                            its samples THERE (red.add.u64) instead of locally          */
 } rt_render_opts;
 
-enum { RT_RENDER_DEFAULT = 0 };
+enum {
+  RT_RENDER_DEFAULT = 0,
+  RT_RENDER_COUNTERS = 1 /* instrumented kernel: also fills rt_stats.census (slower; not for timing) */
+};
 
 /* Asynchronous on the context's stream.  Accumulates fixed-point (2^-32) int64 RGB
  * sums per pixel: integer addition is associative, so the image is bit-identical for
@@ -242,6 +245,12 @@ typedef struct rt_stats {
   int32_t n_media;
   int32_t bvh_nodes_in_smem;
   int32_t kernel_launches; /* number of kernels this context has launched              */
+  /* RT_RENDER_COUNTERS only, since the last clear — the N_* of the roofline model:
+   * [0] BVH node visits (2 box tests each) [1] sphere tests [2] sphere hits [3] quad tests
+   * [4] quad tests past the plane/t early-outs [5] medium tests [6..10] scatters by material
+   * (lambertian, metal, dielectric, diffuse_light, isotropic) [11] checker [12] image
+   * [13] noise texture evaluations                                                      */
+  uint64_t census[14];
 } rt_stats;
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 

@@ -166,8 +166,8 @@ class Context:
     def upload_scene(self, desc):
         self._check(self._lib.rt_upload_scene(self._h, desc), "rt_upload_scene")
 
-    def render(self, cam, seed=0, sample_begin=0, sample_count=0, clear=True, peer_accum=None):
-        o = _abi.rt_render_opts(seed, sample_begin, sample_count, 1 if clear else 0, 0, peer_accum)
+    def render(self, cam, seed=0, sample_begin=0, sample_count=0, clear=True, peer_accum=None, flags=0):
+        o = _abi.rt_render_opts(seed, sample_begin, sample_count, 1 if clear else 0, flags, peer_accum)
         self._check(self._lib.rt_render(self._h, C.byref(cam), C.byref(o)), "rt_render")
 
     def synchronize(self):

@@ -53,6 +53,7 @@ __device__ __forceinline__ long long to_fixed(float v) {
   return __float2ll_rn(v * kFixScale);
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
@@ -67,6 +68,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   int pixel = -1, px = 0, py = 0, s = 0, s_end = 0;
   bool alive = false;
   unsigned int n_rays = 0, n_samples = 0;
+  unsigned int cn[COUNT ? CN_COUNT : 1];
+  if (COUNT)
+    for (int i = 0; i < CN_COUNT; i++) cn[i] = 0;
   PathKey key{P.key, 0u, 0u};
   float3 o = f3(0, 0, 0), d = f3(0, 0, 1), beta = f3(1, 1, 1), L = f3(0, 0, 0);
   float time = 0.0f;
@@ -132,14 +136,14 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     n_rays++;
     uint4 rnd = rng_block(key, bounce, 0u);
     MediumRng mr{&key, bounce, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
-    Hit h = closest_hit(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr);
+    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr, cn);
     if (h.ref == REF_NONE) {
       L = L + beta * P.cam.bg;
       alive = false;
     } else {
       Surface sf = surface_at(sc, h, o, d, time);
       float3 emit, atten, d_out;
-      bool cont = scatter_ray(sc, sf, d, rnd, emit, atten, d_out);
+      bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
       L = L + beta * emit;
       if (cont) {
         beta = beta * atten;
@@ -168,6 +172,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     atomicAdd(P.counters + 1, (unsigned long long)rays);
     atomicAdd(P.counters + 2, (unsigned long long)smp);
   }
+  if (COUNT)
+    for (int i = 0; i < CN_COUNT; i++)
+      if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);
 }
 
 // ---- write_color (common/color.hpp:26-58) on the device, in double like the reference ----
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     MediumRng mr{&key, 1u, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
     bool media = sc.n_media && !(P.flags & RT_TRACE_SKIP_MEDIA);
     float tmaxf = P.tmax < 3e38 ? float(P.tmax) : __int_as_float(0x7f800000);
-    Hit h = closest_hit(sc, ns, o, d, float(tm), float(P.tmin), tmaxf, REF_NONE, media ? &mr : nullptr);
+    Hit h = closest_hit<false>(sc, ns, o, d, float(tm), float(P.tmin), tmaxf, REF_NONE, media ? &mr : nullptr, nullptr);
     if (h.ref != REF_NONE) {
       Surface sf = surface_at(sc, h, o, d, float(tm));
       uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
@@ -349,7 +356,7 @@ __global__ void eval_texture_kernel(DeviceScene sc, int tex, long long n, const 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double* q = uvp + 5 * i;
-  float3 c = texture_value(sc, tex, float(q[0]), float(q[1]), f3(float(q[2]), float(q[3]), float(q[4])));
+  float3 c = texture_value<false>(sc, tex, float(q[0]), float(q[1]), f3(float(q[2]), float(q[3]), float(q[4])), nullptr);
   rgb[3 * i] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
 }
 
@@ -366,7 +373,7 @@ __global__ void eval_scatter_kernel(DeviceScene sc, int material, long long n, u
   PathKey key{make_uint2((unsigned)seed, (unsigned)(seed >> 32)), (uint32_t)i, (uint32_t)(i >> 32)};
   uint4 rnd = rng_block(key, 1u, 0u);
   float3 emit, a = f3(0, 0, 0), dout = f3(0, 0, 0);
-  bool ok = scatter_ray(sc, s, f3(float(dir_in[3 * i]), float(dir_in[3 * i + 1]), float(dir_in[3 * i + 2])), rnd, emit, a, dout);
+  bool ok = scatter_ray<false>(sc, s, f3(float(dir_in[3 * i]), float(dir_in[3 * i + 1]), float(dir_in[3 * i + 2])), rnd, emit, a, dout, nullptr);
   scattered[i] = ok;
   dir_out[3 * i] = dout.x, dir_out[3 * i + 1] = dout.y, dir_out[3 * i + 2] = dout.z;
   atten[3 * i] = a.x, atten[3 * i + 1] = a.y, atten[3 * i + 2] = a.z;
@@ -405,7 +412,7 @@ struct rt_ctx {
   unsigned long long* accum = nullptr;
   size_t accum_values = 0;
   int acc_w = 0, acc_h = 0;
-  unsigned long long* counters = nullptr;  // 4 x u64
+  unsigned long long* counters = nullptr;  // 32 x u64: [0] next item, [1] rays, [2] samples, [4..] census
   unsigned long long rays_total = 0, samples_total = 0;
   int smem_nodes = 0;
   int launches = 0;
@@ -576,8 +583,8 @@ int rt_init(int device, rt_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
-  if ((e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMemset(ctx->counters, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+  if ((e = cudaMalloc(&ctx->counters, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemset(ctx->counters, 0, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
   *out = ctx;
   return RT_OK;
 }
@@ -682,7 +689,7 @@ static int ensure_accum(rt_ctx* ctx, int W, int H, bool clear) {
   }
   if (clear) {
     RT_CUDA(ctx, cudaMemsetAsync(ctx->accum, 0, values * 8, ctx->stream));
-    RT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 32 * sizeof(unsigned long long), ctx->stream));
     ctx->rays_total = ctx->samples_total = 0;
   }
   return RT_OK;
@@ -721,12 +728,16 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   P.counters = ctx->counters;
   P.smem_nodes = ctx->smem_nodes;
   size_t smem = size_t(P.smem_nodes) * 64;
-  RT_CUDA(ctx, cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const bool count = (opts->flags & RT_RENDER_COUNTERS) != 0;
+  RT_CUDA(ctx, cudaFuncSetAttribute(count ? render_kernel<true> : render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   // counters[0] = first item not pre-assigned to a thread
   unsigned long long first = (unsigned long long)threads;
   RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
   RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  render_kernel<<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+  if (count)
+    render_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+  else
+    render_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
   ctx->launches++;
   RT_CUDA(ctx, cudaGetLastError());
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -786,10 +797,11 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::memset(out, 0, sizeof *out);
-  unsigned long long c[4] = {0, 0, 0, 0};
+  unsigned long long c[32];
   RT_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
   out->rays = c[1];
   out->samples = c[2];
+  for (int i = 0; i < 14; i++) out->census[i] = c[4 + i];
   if (ctx->timed) {
     float ms = 0;
     RT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

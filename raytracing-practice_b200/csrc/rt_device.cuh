@@ -226,11 +226,16 @@ struct MediumRng {
 
 constexpr int kStackDepth = 32;
 
+// Census slots of the instrumented build (RT_RENDER_COUNTERS): the N_* of SURVEY.md §8(d).
+enum : int { CN_NODE = 0, CN_SPH = 1, CN_SPH_HIT = 2, CN_QUAD = 3, CN_QUAD_FULL = 4, CN_MEDIUM = 5, CN_LAMB = 6, CN_METAL = 7,
+             CN_DIEL = 8, CN_LIGHT = 9, CN_ISO = 10, CN_TEX_CHECKER = 11, CN_TEX_IMAGE = 12, CN_TEX_NOISE = 13, CN_COUNT = 14 };
+
 // world.hit(r, interval(tmin, tmax), rec): closest hit over the whole scene.
 //   skip_ref: the primitive the ray starts on (REF_NONE for camera rays / medium scatters).
 //   mrng == nullptr: media are transparent.
+template <bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
-                                           uint32_t skip_ref, MediumRng* mrng) {
+                                           uint32_t skip_ref, MediumRng* mrng, unsigned int* cn) {
   // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
   float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
                   fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
@@ -245,6 +250,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
       float4 a, b, c;
       int c0, c1;
       load_node(ns, cur, a, b, c, c0, c1);
+      if (COUNT) cn[CN_NODE]++;
       // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
       float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
       float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
@@ -279,11 +285,20 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
         float t = -1.0f;
         if (type == REF_SPHERE) {
           t = hit_sphere(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, tmin, best.t, ref == skip_ref);
+          if (COUNT) cn[CN_SPH]++, cn[CN_SPH_HIT] += t != -1.0f;
         } else if (type == REF_QUAD) {
-          if (ref != skip_ref) t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, tmin, best.t);
+          if (ref != skip_ref) {
+            t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, tmin, best.t);
+            if (COUNT) {
+              float4 nD = __ldg(sc.quads + 3 * idx);  // "full" = got past the plane / t-range early-outs
+              float den = dot(xyz(nD), d), tq = (nD.w - dot(xyz(nD), o)) / den;
+              cn[CN_QUAD]++, cn[CN_QUAD_FULL] += fabsf(den) >= 1e-8f && tq >= tmin && tq <= best.t || t != -1.0f;
+            }
+          }
         } else if (ref != REF_NONE && mrng) {
           const DMedium m = sc.media[idx];
           t = medium_sample(sc, m, o, d, time, tmin, best.t, mrng->get(int(idx)));
+          if (COUNT) cn[CN_MEDIUM]++;
         }
         if (t != -1.0f) best = Hit{t, ref};
       }
@@ -340,7 +355,8 @@ __device__ __forceinline__ float2 sphere_uv(float3 n) {
   return make_float2(phi * (0.5f / PI), theta * (1.0f / PI));
 }
 
-__device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p) {
+template <bool COUNT>
+__device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p, unsigned int* cn) {
 #pragma unroll 1
   for (int guard = 0; guard < 16; guard++) {
     float4 t0 = __ldg(sc.textures + 2 * tex), t1 = __ldg(sc.textures + 2 * tex + 1);
@@ -349,10 +365,12 @@ __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, 
     if (kind == TEX_CHECKER) {  // texture.hpp:57-79 ; (sum % 2 == 0) == ((sum & 1) == 0) for negatives too
       int s = int(floorf(t0.w * p.x)) + int(floorf(t0.w * p.y)) + int(floorf(t0.w * p.z));
       tex = (s & 1) ? b : a;
+      if (COUNT) cn[CN_TEX_CHECKER]++;
       continue;
     }
     if (kind == TEX_IMAGE) {  // texture.hpp:97-118 + rtw_stb_image.hpp:104-134
       int4 im = __ldg(sc.images + a);
+      if (COUNT) cn[CN_TEX_IMAGE]++;
       if (im.z <= 0) return f3(0.0f, 1.0f, 1.0f);
       u = fminf(fmaxf(u, 0.0f), 1.0f);
       v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
@@ -363,6 +381,7 @@ __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, 
       return f3(s * px.x, s * px.y, s * px.z);
     }
     // TEX_NOISE: marble, texture.hpp:150
+    if (COUNT) cn[CN_TEX_NOISE]++;
     float turb = perlin_turb(sc.perlin_vec + 256 * a, sc.perlin_perm + 768 * a, p);
     float g = 0.5f * (1.0f + sinf(fmaf(t0.w, p.z, 10.0f * turb)));
     return f3(g, g, g);
@@ -423,16 +442,19 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
 }
 
 // returns true when the path continues along (o, d); `emit` is material::emitted.
-__device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out) {
+template <bool COUNT>
+__device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out,
+                                            unsigned int* cn) {
   float4 m0 = __ldg(sc.materials + 2 * s.material), m1 = __ldg(sc.materials + 2 * s.material + 1);
   int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
   emit = f3(0.0f, 0.0f, 0.0f);
+  if (COUNT) cn[CN_LAMB + (kind - MAT_LAMBERTIAN)]++;
   switch (kind) {
     case MAT_LAMBERTIAN: {  // material.hpp:51-71
       float3 dir = s.n + unit_vector_from(u01(rnd.x), u01(rnd.y));
       if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
       d_out = dir;
-      atten = texture_value(sc, tex, s.u, s.v, s.p);
+      atten = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
       return true;
     }
     case MAT_METAL: {  // material.hpp:86-106
@@ -464,11 +486,11 @@ __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface
       return true;
     }
     case MAT_LIGHT:  // material.hpp:223-240: emits on both faces, never scatters
-      emit = texture_value(sc, tex, s.u, s.v, s.p);
+      emit = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
       return false;
     default:  // MAT_ISOTROPIC, SURVEY B.3
       d_out = unit_vector_from(u01(rnd.x), u01(rnd.y));
-      atten = texture_value(sc, tex, s.u, s.v, s.p);
+      atten = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
       return true;
   }
 }
