@@ -86,6 +86,8 @@ struct DeviceScene {
   const XOp* xops;
   const int2* xchains;  // {first op, n ops}
   int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures;
+  int n_global_media;   // media that enclose the whole scene: sampled once per ray, not via the BVH
+  int global_media[4];
   float scene_abs_max;  // max |coordinate| of any finite bound (conservative-cull epsilon scale)
 };
 

@@ -77,8 +77,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   int depth = 0;
   uint32_t bounce = 1, skip = REF_NONE;
 
+  // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
+  // boundary is a warp vote, so the 32 lanes reconverge here; lanes that ran out of work idle
+  // until the whole warp is done (only at the very end of the render).
+  const unsigned FULL = 0xFFFFFFFFu;
+  bool done = false;
   for (;;) {
-    if (!alive) {
+    if (!alive && !done) {
       if (s == s_end) {
         if (pixel >= 0) {  // flush the finished item
           unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
@@ -104,62 +109,72 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
             pixel = -1;
           }
         }
-        if (!got) break;
+        done = !got;
         key.pixel = uint32_t(pixel);
       }
-      // ---- camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time ----
-      key.sample = uint32_t(s++);
-      n_samples++;
-      uint4 r0 = rng_block(key, 0u, 0u);
-      float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
-      time = u01(r0.z);
-      float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
-      o = P.cam.center;
-      if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
-        uint4 r1 = rng_block(key, 0u, 1u);
-        float rr = sqrtf(u01(r1.x)), sn, cs;
-        sincospif(2.0f * u01(r1.y), &sn, &cs);
-        float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
-        o = o + off;
-        dir = dir - off;
+      if (!done) {
+        // ---- camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time ----
+        key.sample = uint32_t(s++);
+        n_samples++;
+        uint4 r0 = rng_block(key, 0u, 0u);
+        float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
+        time = u01(r0.z);
+        float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
+        o = P.cam.center;
+        if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
+          uint4 r1 = rng_block(key, 0u, 1u);
+          float rr = sqrtf(u01(r1.x)), sn, cs;
+          sincospif(2.0f * u01(r1.y), &sn, &cs);
+          float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
+          o = o + off;
+          dir = dir - off;
+        }
+        d = dir;
+        beta = f3(1.0f, 1.0f, 1.0f);
+        L = f3(0.0f, 0.0f, 0.0f);
+        depth = P.cam.max_depth;
+        bounce = 1;
+        skip = REF_NONE;
+        alive = depth > 0;  // max_depth <= 0: ray_color returns black at once (camera.hpp:183-186)
       }
-      d = dir;
-      beta = f3(1.0f, 1.0f, 1.0f);
-      L = f3(0.0f, 0.0f, 0.0f);
-      depth = P.cam.max_depth;
-      bounce = 1;
-      skip = REF_NONE;
-      alive = depth > 0;
-      if (!alive) continue;
+    }
+    if (!__any_sync(FULL, alive)) {
+      if (__all_sync(FULL, done)) break;
+      continue;
     }
     // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
-    n_rays++;
-    uint4 rnd = rng_block(key, bounce, 0u);
-    MediumRng mr{&key, bounce, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
-    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr, cn);
-    if (h.ref == REF_NONE) {
-      L = L + beta * P.cam.bg;
-      alive = false;
-    } else {
-      Surface sf = surface_at(sc, h, o, d, time);
-      float3 emit, atten, d_out;
-      bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
-      L = L + beta * emit;
-      if (cont) {
-        beta = beta * atten;
-        o = sf.p;
-        d = d_out;
-        skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
-        bounce++;
-        alive = --depth > 0;
-      } else {
-        alive = false;
-      }
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (alive) {
+      n_rays++;
+      rnd = rng_block(key, bounce, 0u);
     }
-    if (!alive) {
-      acc_r += to_fixed(L.x);
-      acc_g += to_fixed(L.y);
-      acc_b += to_fixed(L.z);
+    MediumRng mr{&key, bounce, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
+    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr, cn, alive);
+    if (alive) {
+      if (h.ref == REF_NONE) {
+        L = L + beta * P.cam.bg;
+        alive = false;
+      } else {
+        Surface sf = surface_at(sc, h, o, d, time);
+        float3 emit, atten, d_out;
+        bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
+        L = L + beta * emit;
+        if (cont) {
+          beta = beta * atten;
+          o = sf.p;
+          d = d_out;
+          skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
+          bounce++;
+          alive = --depth > 0;
+        } else {
+          alive = false;
+        }
+      }
+      if (!alive) {
+        acc_r += to_fixed(L.x);
+        acc_g += to_fixed(L.y);
+        acc_b += to_fixed(L.z);
+      }
     }
   }
   // ---- counters: warp-reduce, one atomic per warp ---------------------------------------
@@ -652,6 +667,8 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.n_materials = int(h.materials.size() / 2);
   s.n_textures = int(h.textures.size() / 2);
   s.scene_abs_max = h.scene_abs_max;
+  s.n_global_media = int(h.global_media.size());
+  for (int i = 0; i < 4; i++) s.global_media[i] = i < s.n_global_media ? h.global_media[size_t(i)] : -1;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // top of the BVH in shared memory: as many breadth-first nodes as fit beside the static needs
   size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 0;

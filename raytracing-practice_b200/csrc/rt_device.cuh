@@ -233,52 +233,86 @@ enum : int { CN_NODE = 0, CN_SPH = 1, CN_SPH_HIT = 2, CN_QUAD = 3, CN_QUAD_FULL 
 // world.hit(r, interval(tmin, tmax), rec): closest hit over the whole scene.
 //   skip_ref: the primitive the ray starts on (REF_NONE for camera rays / medium scatters).
 //   mrng == nullptr: media are transparent.
+//   active: lanes without a ray pass false and idle through the loops.
+//
+// MUST be called with all 32 lanes of the warp converged (exited lanes excepted).  The loops are
+// "while-while" (Aila & Laine): every lane walks internal nodes until ALL lanes sit on a leaf, then
+// the leaves are intersected together.  Loop boundaries are warp votes (__any_sync with the full
+// mask), which force the lanes to reconverge every iteration; with plain per-lane `continue`s
+// the compiler never re-merged them and ncu showed 4.7 of 32 lanes active per instruction
+// (profiles/r01_render_divergent.md).
 template <bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
-                                           uint32_t skip_ref, MediumRng* mrng, unsigned int* cn) {
+                                           uint32_t skip_ref, MediumRng* mrng, unsigned int* cn, bool active = true) {
+  const unsigned FULL = 0xFFFFFFFFu;
   // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
   float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
                   fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
   float3 ood = o * inv;
   Hit best{tmax, REF_NONE};
+  // media whose boundary encloses the whole scene (the r=5000 fog of the Book-2 final scene) are
+  // met by every ray: sample them here, converged, instead of as a divergent BVH leaf
+  if (mrng && active) {
+    for (int g = 0; g < sc.n_global_media; g++) {
+      const int mi = sc.global_media[g];
+      const DMedium m = sc.media[mi];
+      float t = medium_sample(sc, m, o, d, time, tmin, best.t, mrng->get(mi));
+      if (COUNT) cn[CN_MEDIUM]++;
+      if (t != -1.0f) best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
+    }
+  }
   int stack[kStackDepth];
   float stack_t[kStackDepth];
   int sp = 0;
   int cur = 0;
-  for (;;) {
-    if (cur >= 0) {
-      float4 a, b, c;
-      int c0, c1;
-      load_node(ns, cur, a, b, c, c0, c1);
-      if (COUNT) cn[CN_NODE]++;
-      // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
-      float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
-      float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
-      float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
-      float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-      float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
-      x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
-      y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
-      z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
-      float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-      float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
-      bool h0 = n0 <= f0, h1 = n1 <= f1;
-      if (h0 && h1) {
-        bool first0 = n0 <= n1;
-        if (sp < kStackDepth) {
-          stack[sp] = first0 ? c1 : c0;
-          stack_t[sp] = first0 ? n1 : n0;
-          sp++;
+  bool trav = active;
+  while (__any_sync(FULL, trav)) {
+    // ---- internal nodes, until every lane is on a leaf (or finished) ----------------------
+    while (__any_sync(FULL, trav && cur >= 0)) {
+      if (trav && cur >= 0) {
+        float4 a, b, c;
+        int c0, c1;
+        load_node(ns, cur, a, b, c, c0, c1);
+        if (COUNT) cn[CN_NODE]++;
+        // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
+        float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
+        float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
+        float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
+        float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+        float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
+        x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
+        y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
+        z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
+        float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+        float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
+        const bool h0 = n0 <= f0, h1 = n1 <= f1;
+        if (h0 && h1) {
+          const bool first0 = n0 <= n1;
+          if (sp < kStackDepth) {
+            stack[sp] = first0 ? c1 : c0;
+            stack_t[sp] = first0 ? n1 : n0;
+            sp++;
+          }
+          cur = first0 ? c0 : c1;
+        } else if (h0 || h1) {
+          cur = h0 ? c0 : c1;
+        } else {  // pop, skipping subtrees that start beyond the current closest hit
+          trav = false;
+          while (sp > 0) {
+            sp--;
+            if (stack_t[sp] <= best.t) {
+              cur = stack[sp];
+              trav = true;
+              break;
+            }
+          }
         }
-        cur = first0 ? c0 : c1;
-        continue;
       }
-      if (h0) { cur = c0; continue; }
-      if (h1) { cur = c1; continue; }
-    } else {
-      // leaf: ~cur = (first << 3) | (count - 1)
-      int code = ~cur;
-      int first = code >> 3, count = (code & 7) + 1;
+    }
+    // ---- leaves: ~cur = (first << 3) | (count - 1) -----------------------------------------
+    if (trav) {
+      const int code = ~cur;
+      const int first = code >> 3, count = (code & 7) + 1;
       for (int k = 0; k < count; k++) {
         uint32_t ref = __ldg(sc.leaf_refs + first + k);
         uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
@@ -292,7 +326,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
             if (COUNT) {
               float4 nD = __ldg(sc.quads + 3 * idx);  // "full" = got past the plane / t-range early-outs
               float den = dot(xyz(nD), d), tq = (nD.w - dot(xyz(nD), o)) / den;
-              cn[CN_QUAD]++, cn[CN_QUAD_FULL] += fabsf(den) >= 1e-8f && tq >= tmin && tq <= best.t || t != -1.0f;
+              cn[CN_QUAD]++, cn[CN_QUAD_FULL] += (fabsf(den) >= 1e-8f && tq >= tmin && tq <= best.t) || t != -1.0f;
             }
           }
         } else if (ref != REF_NONE && mrng) {
@@ -302,14 +336,18 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
         }
         if (t != -1.0f) best = Hit{t, ref};
       }
-    }
-    // pop, skipping subtrees that start beyond the current closest hit
-    for (;;) {
-      if (sp == 0) return best;
-      sp--;
-      if (stack_t[sp] <= best.t) { cur = stack[sp]; break; }
+      trav = false;
+      while (sp > 0) {
+        sp--;
+        if (stack_t[sp] <= best.t) {
+          cur = stack[sp];
+          trav = true;
+          break;
+        }
+      }
     }
   }
+  return best;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -49,6 +49,7 @@ struct HostScene {
   std::vector<XQuad> xquads;
   std::vector<XOp> xops;
   std::vector<int2> xchains;
+  std::vector<int> global_media;  // media enclosing every other item (at most 4)
   float scene_abs_max = 1.0f;
   int bvh_depth = 0;
   double sah_cost = 0;
@@ -464,6 +465,26 @@ inline bool build_host_scene(const rt_scene_desc* d, HostScene& out) {
   b.d = d;
   b.out = &out;
   if (!b.visit(d->root, Xform())) return false;
+
+  // A medium whose boundary box contains every other item (the Book-2 scene's r=5000 fog) is met by
+  // every ray: take it out of the BVH and let the kernel sample it once per ray, warp-converged.
+  if (b.items.size() > 1) {
+    for (size_t i = 0; i < b.items.size() && out.global_media.size() < 4;) {
+      const Item& it = b.items[i];
+      bool encloses = (it.ref >> 30) == REF_MEDIUM;
+      for (size_t j = 0; j < b.items.size() && encloses; j++) {
+        if (j == i) continue;
+        for (int a = 0; a < 3; a++)
+          if (b.items[j].box.lo[a] < it.box.lo[a] || b.items[j].box.hi[a] > it.box.hi[a]) encloses = false;
+      }
+      if (encloses) {
+        out.global_media.push_back(int(it.ref & 0x3FFFFFFFu));
+        b.items.erase(b.items.begin() + long(i));
+      } else {
+        i++;
+      }
+    }
+  }
 
   float amax = 1.0f;
   for (const Item& it : b.items)
