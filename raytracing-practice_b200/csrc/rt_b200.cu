@@ -77,43 +77,94 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   int depth = 0;
   uint32_t bounce = 1, skip = REF_NONE;
 
-  // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
-  // boundary is a warp vote, so the 32 lanes reconverge here; lanes that ran out of work idle
-  // until the whole warp is done (only at the very end of the render).
+  // ---- the warp as a tiny wavefront scheduler ---------------------------------------------------
+  // Each lane is a state machine: SHADE (resolve the finished segment, scatter or regenerate a camera
+  // path, start the next query) -> NODE (one BVH node) <-> LEAF (one leaf's primitives) -> SHADE ...
+  // Every iteration the warp ballots the lane modes and executes ONLY the most populated one, so an
+  // instruction is always issued for the largest possible group of lanes and nobody waits for the
+  // warp's slowest ray: a lane whose ray ends early queues for shading while the others keep
+  // traversing.  The ballots are full-mask votes, so the lanes reconverge every iteration.
   const unsigned FULL = 0xFFFFFFFFu;
-  bool done = false;
+  const bool media = sc.n_media != 0;
+  TravState ts;
+  TravStack st;
+  ts.best = Hit{INF, REF_NONE};
+  int mode = MODE_SHADE;
+  bool pending = false;  // a finished closest-hit query is waiting to be shaded
   for (;;) {
-    if (!alive && !done) {
-      if (s == s_end) {
-        if (pixel >= 0) {  // flush the finished item
-          unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
-          if (acc_r) atomicAdd(dst + 0, (unsigned long long)acc_r);
-          if (acc_g) atomicAdd(dst + 1, (unsigned long long)acc_g);
-          if (acc_b) atomicAdd(dst + 2, (unsigned long long)acc_b);
-          acc_r = acc_g = acc_b = 0;
-          pixel = -1;
-        }
-        bool got = false;
-        while (item < P.n_items) {
-          unsigned long long chunk = item / per_chunk, q = item % per_chunk;
-          unsigned int tile = (unsigned int)(q >> 5), lane = (unsigned int)(q & 31u);
-          px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
-          py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
-          item = atomicAdd(P.counters, 1ull);  // my next candidate
-          if (px < P.cam.W && py < P.cam.H) {
-            pixel = py * P.cam.W + px;
-            s = P.sample_begin + int(chunk) * P.chunk;
-            s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
-            got = s < s_end;
-            if (got) break;
-            pixel = -1;
+    const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF),
+                   bS = __ballot_sync(FULL, mode == MODE_SHADE);
+    if ((bN | bL | bS) == 0u) break;
+    const int nN = __popc(bN), nL = __popc(bL), nS = __popc(bS);
+    if (nN >= nL && nN >= nS) {
+      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    } else if (nL >= nS) {
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
+    } else if (mode == MODE_SHADE) {
+      // ---- the tail of one ray_color level (camera.hpp:192-231) -----------------------------
+      if (pending) {
+        pending = false;
+        const Hit h = ts.best;
+        if (h.ref == REF_NONE) {
+          L = L + beta * P.cam.bg;
+          alive = false;
+        } else {
+          const uint4 rnd = rng_block(key, bounce, 0u);
+          Surface sf = surface_at(sc, h, ts.o, ts.d, time);
+          float3 emit, atten, d_out;
+          bool cont = scatter_ray<COUNT>(sc, sf, ts.d, rnd, emit, atten, d_out, cn);
+          L = L + beta * emit;
+          if (cont) {
+            beta = beta * atten;
+            o = sf.p;
+            d = d_out;
+            skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
+            bounce++;
+            alive = --depth > 0;
+          } else {
+            alive = false;
           }
         }
-        done = !got;
-        key.pixel = uint32_t(pixel);
+        if (!alive) {
+          acc_r += to_fixed(L.x);
+          acc_g += to_fixed(L.y);
+          acc_b += to_fixed(L.z);
+        }
       }
-      if (!done) {
-        // ---- camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time ----
+      // ---- path regeneration: next sample of my item, or the next item ------------------------
+      while (!alive && mode != MODE_DONE) {
+        if (s == s_end) {
+          if (pixel >= 0) {  // flush the finished item
+            unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
+            if (acc_r) atomicAdd(dst + 0, (unsigned long long)acc_r);
+            if (acc_g) atomicAdd(dst + 1, (unsigned long long)acc_g);
+            if (acc_b) atomicAdd(dst + 2, (unsigned long long)acc_b);
+            acc_r = acc_g = acc_b = 0;
+            pixel = -1;
+          }
+          bool got = false;
+          while (item < P.n_items) {
+            unsigned long long chunk = item / per_chunk, q = item % per_chunk;
+            unsigned int tile = (unsigned int)(q >> 5), lane = (unsigned int)(q & 31u);
+            px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
+            py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
+            item = atomicAdd(P.counters, 1ull);  // my next candidate
+            if (px < P.cam.W && py < P.cam.H) {
+              pixel = py * P.cam.W + px;
+              s = P.sample_begin + int(chunk) * P.chunk;
+              s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
+              got = s < s_end;
+              if (got) break;
+              pixel = -1;
+            }
+          }
+          if (!got) {
+            mode = MODE_DONE;
+            break;
+          }
+          key.pixel = uint32_t(pixel);
+        }
+        // camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time
         key.sample = uint32_t(s++);
         n_samples++;
         uint4 r0 = rng_block(key, 0u, 0u);
@@ -137,43 +188,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         skip = REF_NONE;
         alive = depth > 0;  // max_depth <= 0: ray_color returns black at once (camera.hpp:183-186)
       }
-    }
-    if (!__any_sync(FULL, alive)) {
-      if (__all_sync(FULL, done)) break;
-      continue;
-    }
-    // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (alive) {
-      n_rays++;
-      rnd = rng_block(key, bounce, 0u);
-    }
-    MediumRng mr{&key, bounce, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
-    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, sc.n_media ? &mr : nullptr, cn, alive);
-    if (alive) {
-      if (h.ref == REF_NONE) {
-        L = L + beta * P.cam.bg;
-        alive = false;
-      } else {
-        Surface sf = surface_at(sc, h, o, d, time);
-        float3 emit, atten, d_out;
-        bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
-        L = L + beta * emit;
-        if (cont) {
-          beta = beta * atten;
-          o = sf.p;
-          d = d_out;
-          skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
-          bounce++;
-          alive = --depth > 0;
-        } else {
-          alive = false;
-        }
-      }
-      if (!alive) {
-        acc_r += to_fixed(L.x);
-        acc_g += to_fixed(L.y);
-        acc_b += to_fixed(L.z);
+      // ---- world.hit(r, interval(0.001, infinity), rec) for the next segment (camera.hpp:192) ----
+      if (mode != MODE_DONE) {
+        n_rays++;
+        mode = trav_begin<COUNT>(ts, sc, o, d, time, 0.001f, INF, skip, media, key, bounce, cn);
+        pending = true;
       }
     }
   }
@@ -321,10 +340,9 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     float3 o = f3(float(P.origin[3 * i]), float(P.origin[3 * i + 1]), float(P.origin[3 * i + 2]));
     float3 d = f3(float(P.direction[3 * i]), float(P.direction[3 * i + 1]), float(P.direction[3 * i + 2]));
     PathKey key{make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32)), (uint32_t)i, 0u};
-    MediumRng mr{&key, 1u, 0xFFFFFFFFu, make_uint4(0, 0, 0, 0)};
     bool media = sc.n_media && !(P.flags & RT_TRACE_SKIP_MEDIA);
     float tmaxf = P.tmax < 3e38 ? float(P.tmax) : __int_as_float(0x7f800000);
-    Hit h = closest_hit<false>(sc, ns, o, d, float(tm), float(P.tmin), tmaxf, REF_NONE, media ? &mr : nullptr, nullptr);
+    Hit h = closest_hit<false>(sc, ns, o, d, float(tm), float(P.tmin), tmaxf, REF_NONE, media, key, 1u, nullptr);
     if (h.ref != REF_NONE) {
       Surface sf = surface_at(sc, h, o, d, float(tm));
       uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;

@@ -206,23 +206,13 @@ __device__ __forceinline__ float medium_sample(const DeviceScene& sc, const DMed
   return t1 + hit_distance / len;
 }
 
-// Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2).
-struct MediumRng {
-  const PathKey* key;
-  uint32_t bounce;
-  uint32_t cached_stream;
-  uint4 cached;
-  __device__ __forceinline__ float get(int medium) {
-    uint32_t stream = 1u + (uint32_t(medium) >> 2);
-    if (stream != cached_stream) {
-      cached = rng_block(*key, bounce, stream);
-      cached_stream = stream;
-    }
-    uint32_t c = uint32_t(medium) & 3u;
-    uint32_t v = c == 0 ? cached.x : (c == 1 ? cached.y : (c == 2 ? cached.z : cached.w));
-    return u01(v);
-  }
-};
+// Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2)
+// of the ray's (pixel, sample, bounce) counter.
+__device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bounce, int medium) {
+  uint4 r = rng_block(key, bounce, 1u + (uint32_t(medium) >> 2));
+  uint32_t c = uint32_t(medium) & 3u;
+  return u01(c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w)));
+}
 
 constexpr int kStackDepth = 32;
 
@@ -230,124 +220,155 @@ constexpr int kStackDepth = 32;
 enum : int { CN_NODE = 0, CN_SPH = 1, CN_SPH_HIT = 2, CN_QUAD = 3, CN_QUAD_FULL = 4, CN_MEDIUM = 5, CN_LAMB = 6, CN_METAL = 7,
              CN_DIEL = 8, CN_LIGHT = 9, CN_ISO = 10, CN_TEX_CHECKER = 11, CN_TEX_IMAGE = 12, CN_TEX_NOISE = 13, CN_COUNT = 14 };
 
-// world.hit(r, interval(tmin, tmax), rec): closest hit over the whole scene.
-//   skip_ref: the primitive the ray starts on (REF_NONE for camera rays / medium scatters).
-//   mrng == nullptr: media are transparent.
-//   active: lanes without a ray pass false and idle through the loops.
-//
-// MUST be called with all 32 lanes of the warp converged (exited lanes excepted).  The loops are
-// "while-while" (Aila & Laine): every lane walks internal nodes until ALL lanes sit on a leaf, then
-// the leaves are intersected together.  Loop boundaries are warp votes (__any_sync with the full
-// mask), which force the lanes to reconverge every iteration; with plain per-lane `continue`s
-// the compiler never re-merged them and ncu showed 4.7 of 32 lanes active per instruction
-// (profiles/r01_render_divergent.md).
+// ---------------------------------------------------------------------------------------
+// world.hit(r, interval(tmin, tmax), rec) as a per-lane state machine.
+//   bvh_node::hit + aabb::hit  -> node_step  (one BVH2 node: both children's slab tests)
+//   hittable_list::hit over leaves, sphere::hit / quad::hit / constant_medium::hit -> leaf_step
+// A lane is in one of these modes; the CALLER decides which step the warp executes next
+// (closest_hit: while-while; render_kernel: the most populated mode wins), so the same
+// traversal code serves the parity queries and the production megakernel.
+enum : int { MODE_SHADE = 0, MODE_NODE = 1, MODE_LEAF = 2, MODE_DONE = 3 };
+
+struct TravState {
+  float3 o, d, inv, ood;
+  float time, tmin;
+  Hit best;
+  uint32_t skip;  // the primitive the ray starts on (REF_NONE for camera rays / medium scatters)
+  int cur, sp;
+};
+// The traversal stack is kept OUT of TravState (two plain local arrays) so that the scalars above
+// are promoted to registers; only the dynamically indexed stack lives in local memory (L1).
+struct TravStack {
+  int node[kStackDepth];
+  float t[kStackDepth];
+};
+
+// pop, skipping subtrees that start beyond the current closest hit
+__device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
+  while (ts.sp > 0) {
+    ts.sp--;
+    if (st.t[ts.sp] <= ts.best.t) {
+      ts.cur = st.node[ts.sp];
+      return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
+    }
+  }
+  return MODE_SHADE;  // traversal finished: ts.best is the answer
+}
+
+// Start a query.  `media`: sample the scene-enclosing media (met by every ray — the r=5000 fog of
+// the Book-2 final scene) right here, where the caller's lanes are converged, not as a BVH leaf.
 template <bool COUNT>
-__device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
-                                           uint32_t skip_ref, MediumRng* mrng, unsigned int* cn, bool active = true) {
-  const unsigned FULL = 0xFFFFFFFFu;
+__device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, float3 o, float3 d, float time, float tmin, float tmax, uint32_t skip,
+                                          bool media, const PathKey& key, uint32_t bounce, unsigned int* cn) {
+  ts.o = o, ts.d = d, ts.time = time, ts.tmin = tmin, ts.skip = skip;
   // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
-  float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
-                  fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
-  float3 ood = o * inv;
-  Hit best{tmax, REF_NONE};
-  // media whose boundary encloses the whole scene (the r=5000 fog of the Book-2 final scene) are
-  // met by every ray: sample them here, converged, instead of as a divergent BVH leaf
-  if (mrng && active) {
+  ts.inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
+              fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+  ts.ood = o * ts.inv;
+  ts.best = Hit{tmax, REF_NONE};
+  if (media) {
     for (int g = 0; g < sc.n_global_media; g++) {
       const int mi = sc.global_media[g];
       const DMedium m = sc.media[mi];
-      float t = medium_sample(sc, m, o, d, time, tmin, best.t, mrng->get(mi));
+      float t = medium_sample(sc, m, o, d, time, tmin, ts.best.t, medium_uniform(key, bounce, mi));
       if (COUNT) cn[CN_MEDIUM]++;
-      if (t != -1.0f) best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
+      if (t != -1.0f) ts.best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
     }
   }
-  int stack[kStackDepth];
-  float stack_t[kStackDepth];
-  int sp = 0;
-  int cur = 0;
-  bool trav = active;
-  while (__any_sync(FULL, trav)) {
-    // ---- internal nodes, until every lane is on a leaf (or finished) ----------------------
-    while (__any_sync(FULL, trav && cur >= 0)) {
-      if (trav && cur >= 0) {
-        float4 a, b, c;
-        int c0, c1;
-        load_node(ns, cur, a, b, c, c0, c1);
-        if (COUNT) cn[CN_NODE]++;
-        // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
-        float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
-        float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
-        float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
-        float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-        float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
-        x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
-        y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
-        z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
-        float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-        float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best.t));
-        const bool h0 = n0 <= f0, h1 = n1 <= f1;
-        if (h0 && h1) {
-          const bool first0 = n0 <= n1;
-          if (sp < kStackDepth) {
-            stack[sp] = first0 ? c1 : c0;
-            stack_t[sp] = first0 ? n1 : n0;
-            sp++;
-          }
-          cur = first0 ? c0 : c1;
-        } else if (h0 || h1) {
-          cur = h0 ? c0 : c1;
-        } else {  // pop, skipping subtrees that start beyond the current closest hit
-          trav = false;
-          while (sp > 0) {
-            sp--;
-            if (stack_t[sp] <= best.t) {
-              cur = stack[sp];
-              trav = true;
-              break;
-            }
-          }
-        }
-      }
+  ts.sp = 0;
+  ts.cur = 0;
+  return MODE_NODE;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const NodeSource& ns, unsigned int* cn) {
+  float4 a, b, c;
+  int c0, c1;
+  load_node(ns, ts.cur, a, b, c, c0, c1);
+  if (COUNT) cn[CN_NODE]++;
+  const float3 inv = ts.inv, ood = ts.ood;
+  // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
+  float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
+  float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
+  float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
+  float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+  float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
+  y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
+  z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
+  float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+  float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  const bool h0 = n0 <= f0, h1 = n1 <= f1;
+  if (h0 && h1) {  // near child first, far child on the stack with its entry distance
+    const bool first0 = n0 <= n1;
+    if (ts.sp < kStackDepth) {
+      st.node[ts.sp] = first0 ? c1 : c0;
+      st.t[ts.sp] = first0 ? n1 : n0;
+      ts.sp++;
     }
-    // ---- leaves: ~cur = (first << 3) | (count - 1) -----------------------------------------
-    if (trav) {
-      const int code = ~cur;
-      const int first = code >> 3, count = (code & 7) + 1;
-      for (int k = 0; k < count; k++) {
-        uint32_t ref = __ldg(sc.leaf_refs + first + k);
-        uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
-        float t = -1.0f;
-        if (type == REF_SPHERE) {
-          t = hit_sphere(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, tmin, best.t, ref == skip_ref);
-          if (COUNT) cn[CN_SPH]++, cn[CN_SPH_HIT] += t != -1.0f;
-        } else if (type == REF_QUAD) {
-          if (ref != skip_ref) {
-            t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, tmin, best.t);
-            if (COUNT) {
-              float4 nD = __ldg(sc.quads + 3 * idx);  // "full" = got past the plane / t-range early-outs
-              float den = dot(xyz(nD), d), tq = (nD.w - dot(xyz(nD), o)) / den;
-              cn[CN_QUAD]++, cn[CN_QUAD_FULL] += (fabsf(den) >= 1e-8f && tq >= tmin && tq <= best.t) || t != -1.0f;
-            }
-          }
-        } else if (ref != REF_NONE && mrng) {
-          const DMedium m = sc.media[idx];
-          t = medium_sample(sc, m, o, d, time, tmin, best.t, mrng->get(int(idx)));
-          if (COUNT) cn[CN_MEDIUM]++;
-        }
-        if (t != -1.0f) best = Hit{t, ref};
-      }
-      trav = false;
-      while (sp > 0) {
-        sp--;
-        if (stack_t[sp] <= best.t) {
-          cur = stack[sp];
-          trav = true;
-          break;
-        }
-      }
-    }
+    ts.cur = first0 ? c0 : c1;
+    return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
   }
-  return best;
+  if (h0 || h1) {
+    ts.cur = h0 ? c0 : c1;
+    return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
+  }
+  return trav_pop(ts, st);
+}
+
+// leaf: ~cur = (first << 3) | (count - 1)
+template <bool COUNT>
+__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn) {
+  const int code = ~ts.cur;
+  const int first = code >> 3, count = (code & 7) + 1;
+  const float3 o = ts.o, d = ts.d;
+  for (int k = 0; k < count; k++) {
+    uint32_t ref = __ldg(sc.leaf_refs + first + k);
+    uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    float t = -1.0f;
+    if (type == REF_SPHERE) {
+      t = hit_sphere(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, ts.time, ts.tmin, ts.best.t, ref == ts.skip);
+      if (COUNT) cn[CN_SPH]++, cn[CN_SPH_HIT] += t != -1.0f;
+    } else if (type == REF_QUAD) {
+      if (ref != ts.skip) {
+        t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, ts.tmin, ts.best.t);
+        if (COUNT) {
+          float4 nD = __ldg(sc.quads + 3 * idx);  // "full" = got past the plane / t-range early-outs
+          float den = dot(xyz(nD), d), tq = (nD.w - dot(xyz(nD), o)) / den;
+          cn[CN_QUAD]++, cn[CN_QUAD_FULL] += (fabsf(den) >= 1e-8f && tq >= ts.tmin && tq <= ts.best.t) || t != -1.0f;
+        }
+      }
+    } else if (ref != REF_NONE && media) {
+      const DMedium m = sc.media[idx];
+      t = medium_sample(sc, m, o, d, ts.time, ts.tmin, ts.best.t, medium_uniform(key, bounce, int(idx)));
+      if (COUNT) cn[CN_MEDIUM]++;
+    }
+    if (t != -1.0f) ts.best = Hit{t, ref};
+  }
+  return trav_pop(ts, st);
+}
+
+// Closest hit for one ray per lane, "while-while" (Aila & Laine): all lanes walk internal nodes
+// until every lane sits on a leaf, then the leaves are intersected together.  Loop boundaries are
+// warp votes with the full mask, which force reconvergence every iteration; MUST be called with
+// the warp converged (exited lanes excepted).  With plain per-lane `continue`s the compiler never
+// re-merged the lanes: ncu showed 4.75 of 32 active per instruction (profiles/r01_*.md).
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
+                                           uint32_t skip_ref, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn, bool active = true) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  TravState ts;
+  TravStack st;
+  int mode = MODE_DONE;
+  ts.best = Hit{tmax, REF_NONE};
+  if (active) mode = trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
+  while (__any_sync(FULL, mode == MODE_NODE || mode == MODE_LEAF)) {
+    while (__any_sync(FULL, mode == MODE_NODE)) {
+      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    }
+    if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
+  }
+  return ts.best;
 }
 
 // ---------------------------------------------------------------------------------------
