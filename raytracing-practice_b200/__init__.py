@@ -19,7 +19,7 @@ from ._abi import *  # noqa: F401,F403
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-CUDA_LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+CUDA_LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")  # RT_B200_LIB: A/B variant builds
 SCENES_LIB_PATH = os.path.join(_HERE, "librtb200_scenes.so")
 
 _cuda_lib = None

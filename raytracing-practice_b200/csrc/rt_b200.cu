@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -38,13 +39,17 @@ struct RenderParams {
   uint2 key;
   int sample_begin, sample_count, chunk, n_chunks;
   int tiles_x, tiles_y;
-  unsigned long long n_items;
+  unsigned int per_chunk;  // work items per sample chunk = tiles_x * tiles_y * 32
+  unsigned int n_items;
   unsigned long long* accum;     // 3 x int64 per pixel (two's complement adds)
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
 };
 
-constexpr int kRenderThreads = 512;
+#ifndef RT_THREADS
+#define RT_THREADS 1024
+#endif
+constexpr int kRenderThreads = RT_THREADS;
 constexpr float kFixScale = 4294967296.0f;  // 2^32
 
 __device__ __forceinline__ long long to_fixed(float v) {
@@ -61,13 +66,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
-  const unsigned long long per_chunk = (unsigned long long)P.tiles_x * P.tiles_y * 32ull;
 
-  unsigned long long item = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long acc_r = 0, acc_g = 0, acc_b = 0;
-  int pixel = -1, px = 0, py = 0, s = 0, s_end = 0;
+  // Per-lane path state, kept small on purpose: the kernel runs 1024 threads per SM (64 registers),
+  // which measured 9-23 % faster than 512 threads with twice the registers (tools/ab_variants.py).
+  unsigned int item = blockIdx.x * blockDim.x + threadIdx.x;  // n_items < 2^32 is checked by the host
+  int pixel = -1, s = 0, s_end = 0;
   bool alive = false;
-  unsigned int n_rays = 0, n_samples = 0;
+  unsigned int n_rays = 0;
   unsigned int cn[COUNT ? CN_COUNT : 1];
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++) cn[i] = 0;
@@ -75,98 +80,43 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   float3 o = f3(0, 0, 0), d = f3(0, 0, 1), beta = f3(1, 1, 1), L = f3(0, 0, 0);
   float time = 0.0f;
   int depth = 0;
-  uint32_t bounce = 1, skip = REF_NONE;
+  uint32_t skip = REF_NONE;
 
-  // ---- the warp as a tiny wavefront scheduler ---------------------------------------------------
-  // Each lane is a state machine: SHADE (resolve the finished segment, scatter or regenerate a camera
-  // path, start the next query) -> NODE (one BVH node) <-> LEAF (one leaf's primitives) -> SHADE ...
-  // Every iteration the warp ballots the lane modes and executes ONLY the most populated one, so an
-  // instruction is always issued for the largest possible group of lanes and nobody waits for the
-  // warp's slowest ray: a lane whose ray ends early queues for shading while the others keep
-  // traversing.  The ballots are full-mask votes, so the lanes reconverge every iteration.
+  // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
+  // boundary is a warp vote, so the 32 lanes reconverge here; lanes that ran out of work idle
+  // until the whole warp is done (only at the very end of the render).
+  // (A finer-grained alternative — every lane a NODE/LEAF/SHADE state machine and the warp executing
+  //  the most populated phase — was measured and lost: same instruction count, lower issue rate;
+  //  profiles/r03_render_phase_sched.md.)
   const unsigned FULL = 0xFFFFFFFFu;
   const bool media = sc.n_media != 0;
-  TravState ts;
-  TravStack st;
-  ts.best = Hit{INF, REF_NONE};
-  int mode = MODE_SHADE;
-  bool pending = false;  // a finished closest-hit query is waiting to be shaded
+  bool done = false;
   for (;;) {
-    const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF),
-                   bS = __ballot_sync(FULL, mode == MODE_SHADE);
-    if ((bN | bL | bS) == 0u) break;
-    const int nN = __popc(bN), nL = __popc(bL), nS = __popc(bS);
-    if (nN >= nL && nN >= nS) {
-      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
-    } else if (nL >= nS) {
-      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
-    } else if (mode == MODE_SHADE) {
-      // ---- the tail of one ray_color level (camera.hpp:192-231) -----------------------------
-      if (pending) {
-        pending = false;
-        const Hit h = ts.best;
-        if (h.ref == REF_NONE) {
-          L = L + beta * P.cam.bg;
-          alive = false;
-        } else {
-          const uint4 rnd = rng_block(key, bounce, 0u);
-          Surface sf = surface_at(sc, h, ts.o, ts.d, time);
-          float3 emit, atten, d_out;
-          bool cont = scatter_ray<COUNT>(sc, sf, ts.d, rnd, emit, atten, d_out, cn);
-          L = L + beta * emit;
-          if (cont) {
-            beta = beta * atten;
-            o = sf.p;
-            d = d_out;
-            skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
-            bounce++;
-            alive = --depth > 0;
-          } else {
-            alive = false;
-          }
-        }
-        if (!alive) {
-          acc_r += to_fixed(L.x);
-          acc_g += to_fixed(L.y);
-          acc_b += to_fixed(L.z);
-        }
-      }
-      // ---- path regeneration: next sample of my item, or the next item ------------------------
-      while (!alive && mode != MODE_DONE) {
-        if (s == s_end) {
-          if (pixel >= 0) {  // flush the finished item
-            unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
-            if (acc_r) atomicAdd(dst + 0, (unsigned long long)acc_r);
-            if (acc_g) atomicAdd(dst + 1, (unsigned long long)acc_g);
-            if (acc_b) atomicAdd(dst + 2, (unsigned long long)acc_b);
-            acc_r = acc_g = acc_b = 0;
-            pixel = -1;
-          }
-          bool got = false;
-          while (item < P.n_items) {
-            unsigned long long chunk = item / per_chunk, q = item % per_chunk;
-            unsigned int tile = (unsigned int)(q >> 5), lane = (unsigned int)(q & 31u);
-            px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
-            py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
-            item = atomicAdd(P.counters, 1ull);  // my next candidate
-            if (px < P.cam.W && py < P.cam.H) {
+    if (!alive && !done) {
+      if (s == s_end) {
+        done = true;
+        while (item < P.n_items) {
+          const unsigned int chunk = item / P.per_chunk, q = item - chunk * P.per_chunk;
+          const unsigned int tile = q >> 5, lane = q & 31u;
+          const int px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
+          const int py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
+          item = (unsigned int)atomicAdd(P.counters, 1ull);  // my next candidate
+          if (px < P.cam.W && py < P.cam.H) {
+            s = P.sample_begin + int(chunk) * P.chunk;
+            s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
+            if (s < s_end) {
               pixel = py * P.cam.W + px;
-              s = P.sample_begin + int(chunk) * P.chunk;
-              s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
-              got = s < s_end;
-              if (got) break;
-              pixel = -1;
+              key.pixel = uint32_t(pixel);
+              done = false;
+              break;
             }
           }
-          if (!got) {
-            mode = MODE_DONE;
-            break;
-          }
-          key.pixel = uint32_t(pixel);
         }
-        // camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time
+      }
+      if (!done) {
+        // ---- camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time ----
         key.sample = uint32_t(s++);
-        n_samples++;
+        const int py = pixel / P.cam.W, px = pixel - py * P.cam.W;
         uint4 r0 = rng_block(key, 0u, 0u);
         float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
         time = u01(r0.z);
@@ -184,28 +134,54 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         beta = f3(1.0f, 1.0f, 1.0f);
         L = f3(0.0f, 0.0f, 0.0f);
         depth = P.cam.max_depth;
-        bounce = 1;
         skip = REF_NONE;
         alive = depth > 0;  // max_depth <= 0: ray_color returns black at once (camera.hpp:183-186)
       }
-      // ---- world.hit(r, interval(0.001, infinity), rec) for the next segment (camera.hpp:192) ----
-      if (mode != MODE_DONE) {
-        n_rays++;
-        mode = trav_begin<COUNT>(ts, sc, o, d, time, 0.001f, INF, skip, media, key, bounce, cn);
-        pending = true;
+    }
+    if (!__any_sync(FULL, alive)) {
+      if (__all_sync(FULL, done)) break;
+      continue;
+    }
+    // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
+    const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;  // Philox counter word: 1, 2, ...
+    if (alive) n_rays++;
+    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive);
+    if (alive) {
+      if (h.ref == REF_NONE) {
+        L = L + beta * P.cam.bg;
+        alive = false;
+      } else {
+        const uint4 rnd = rng_block(key, bounce, 0u);
+        Surface sf = surface_at(sc, h, o, d, time);
+        float3 emit, atten, d_out;
+        bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
+        L = L + beta * emit;
+        if (cont) {
+          beta = beta * atten;
+          o = sf.p;
+          d = d_out;
+          skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
+          alive = --depth > 0;
+        } else {
+          alive = false;
+        }
+      }
+      if (!alive) {
+        // the finished sample, quantised to 2^-32, straight into the int64 accumulator (red.add.u64:
+        // fire-and-forget, ~3 per 5 rays).  Integer adds commute, so the image does not depend on
+        // which lane / CTA / launch / GPU contributed which sample.
+        unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
+        const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
+        if (fr) atomicAdd(dst + 0, (unsigned long long)fr);
+        if (fg) atomicAdd(dst + 1, (unsigned long long)fg);
+        if (fb) atomicAdd(dst + 2, (unsigned long long)fb);
       }
     }
   }
   // ---- counters: warp-reduce, one atomic per warp ---------------------------------------
-  unsigned int rays = n_rays, smp = n_samples;
-  for (int off = 16; off > 0; off >>= 1) {
-    rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
-    smp += __shfl_down_sync(0xFFFFFFFFu, smp, off);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(P.counters + 1, (unsigned long long)rays);
-    atomicAdd(P.counters + 2, (unsigned long long)smp);
-  }
+  unsigned int rays = n_rays;
+  for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
+  if ((threadIdx.x & 31) == 0) atomicAdd(P.counters + 1, (unsigned long long)rays);
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++)
       if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);
@@ -758,7 +734,10 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   long long chunk = total / (threads * 8);
   P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, 32, (long long)P.sample_count})));
   P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
-  P.n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull * (unsigned long long)P.n_chunks;
+  const unsigned long long n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull * (unsigned long long)P.n_chunks;
+  if (n_items >= 0xFFFFFFFFull - (unsigned long long)threads) return fail(ctx, RT_ERR_INVALID, "image x samples too large for one launch: shard the samples");
+  P.per_chunk = unsigned(P.tiles_x) * unsigned(P.tiles_y) * 32u;
+  P.n_items = unsigned(n_items);
   P.accum = opts->peer_accum ? static_cast<unsigned long long*>(opts->peer_accum) : ctx->accum;
   P.counters = ctx->counters;
   P.smem_nodes = ctx->smem_nodes;
@@ -774,6 +753,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   else
     render_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
   ctx->launches++;
+  ctx->samples_total += (unsigned long long)f.image_width * f.image_height * P.sample_count;
   RT_CUDA(ctx, cudaGetLastError());
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -835,7 +815,7 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
   unsigned long long c[32];
   RT_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
   out->rays = c[1];
-  out->samples = c[2];
+  out->samples = ctx->samples_total;  // every sample of the requested range is rendered: W*H*count per launch
   for (int i = 0; i < 14; i++) out->census[i] = c[4 + i];
   if (ctx->timed) {
     float ms = 0;

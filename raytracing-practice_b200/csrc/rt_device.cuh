@@ -215,6 +215,9 @@ __device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bou
 }
 
 constexpr int kStackDepth = 32;
+#ifndef RT_NODE_THR
+#define RT_NODE_THR 1
+#endif
 
 // Census slots of the instrumented build (RT_RENDER_COUNTERS): the N_* of SURVEY.md §8(d).
 enum : int { CN_NODE = 0, CN_SPH = 1, CN_SPH_HIT = 2, CN_QUAD = 3, CN_QUAD_FULL = 4, CN_MEDIUM = 5, CN_LAMB = 6, CN_METAL = 7,
@@ -362,11 +365,16 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
   int mode = MODE_DONE;
   ts.best = Hit{tmax, REF_NONE};
   if (active) mode = trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
-  while (__any_sync(FULL, mode == MODE_NODE || mode == MODE_LEAF)) {
-    while (__any_sync(FULL, mode == MODE_NODE)) {
+  for (;;) {
+    const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF);
+    if ((bN | bL) == 0u) break;
+    // node steps while at least RT_NODE_THR lanes want one (RT_NODE_THR == 1: classic while-while,
+    // the inner loop drains to the last lane); below the threshold the lanes waiting on leaves go first
+    if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
       if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    } else {
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
     }
-    if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
   }
   return ts.best;
 }
