@@ -183,13 +183,31 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mrays_per_s": last[1] / sec / 1e6, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the real stdout (fd 1 is pointed at stderr while we run, so that
+    library banners such as 'NCCL version ...' cannot end up in front of it)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -341,7 +359,7 @@ def main():
             line["speedup_vs_cpu_baseline_1core"] = line["e2e"]["value"] / line["cpu_baseline"]["value"]
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
     if world > 1:
         torch.distributed.destroy_process_group()
