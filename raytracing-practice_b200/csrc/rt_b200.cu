@@ -85,9 +85,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
   // boundary is a warp vote, so the 32 lanes reconverge here; lanes that ran out of work idle
   // until the whole warp is done (only at the very end of the render).
-  // (A finer-grained alternative — every lane a NODE/LEAF/SHADE state machine and the warp executing
-  //  the most populated phase — was measured and lost: same instruction count, lower issue rate;
-  //  profiles/r03_render_phase_sched.md.)
+  // (Two finer-grained alternatives were measured and lost, see profiles/r03_render_phase_sched.md:
+  //  every lane a NODE/LEAF/SHADE state machine with the warp executing the most populated phase, and a
+  //  resumable traversal that breaks out to shade/refill finished lanes once < 8..24 lanes still traverse.
+  //  Shading a half-empty warp twice costs more than the shallow traversal saves.)
   const unsigned FULL = 0xFFFFFFFFu;
   const bool media = sc.n_media != 0;
   bool done = false;

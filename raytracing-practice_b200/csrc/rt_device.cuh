@@ -18,6 +18,13 @@
 
 namespace rtb200 {
 
+// Big, rarely executed helpers are kept OUT of line (RT_OUTLINE): the fully inlined megakernel was
+// 4,096 SASS instructions = 64 KB, and with 32 resident warps at scattered PCs the top stall was
+// 'no instruction' (instruction-cache misses), profiles/r04_render_t1024.md.
+#ifndef RT_OUTLINE
+#define RT_OUTLINE __noinline__
+#endif
+
 // ---------------------------------------------------------------------------------------
 // small float3 algebra
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -36,7 +43,10 @@ __device__ __forceinline__ float3 normalize3(float3 a) { return rsqrtf(dot(a, a)
 // Philox-4x32-10 (Salmon et al. 2011), counter-based: the sample set of a (pixel, sample,
 // bounce) is a pure function of the key, so images do not depend on how samples are sharded
 // over threads, launches or GPUs.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#ifndef RT_OUTLINE_PHILOX
+#define RT_OUTLINE_PHILOX RT_OUTLINE
+#endif
+__device__ RT_OUTLINE_PHILOX uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -192,7 +202,7 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
   return t2 != INF;
 }
 
-__device__ __forceinline__ float medium_sample(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float tmin, float tmax, float u) {
+__device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float tmin, float tmax, float u) {
   float t1, t2;
   if (!medium_span(sc, m, o, d, time, t1, t2)) return -1.0f;
   t1 = fmaxf(t1, tmin);
@@ -403,7 +413,7 @@ __device__ __forceinline__ float perlin_noise(const float4* __restrict__ vec, co
   return accum;
 }
 
-__device__ __forceinline__ float perlin_turb(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {
+__device__ RT_OUTLINE float perlin_turb(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {
   float accum = 0.0f, weight = 1.0f;
 #pragma unroll 1
   for (int i = 0; i < 7; i++) {  // noise.turb(p, 7), texture.hpp:150
@@ -513,20 +523,24 @@ template <bool COUNT>
 __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out,
                                             unsigned int* cn) {
   float4 m0 = __ldg(sc.materials + 2 * s.material), m1 = __ldg(sc.materials + 2 * s.material + 1);
-  int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
+  const int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
   emit = f3(0.0f, 0.0f, 0.0f);
   if (COUNT) cn[CN_LAMB + (kind - MAT_LAMBERTIAN)]++;
+  // one texture call site and one unit-vector site for all materials (code size: see RT_OUTLINE)
+  float3 tv = f3(1.0f, 1.0f, 1.0f);
+  if (tex >= 0) tv = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
+  const float3 rv = unit_vector_from(u01(rnd.x), u01(rnd.y));
   switch (kind) {
     case MAT_LAMBERTIAN: {  // material.hpp:51-71
-      float3 dir = s.n + unit_vector_from(u01(rnd.x), u01(rnd.y));
+      float3 dir = s.n + rv;
       if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
       d_out = dir;
-      atten = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
+      atten = tv;
       return true;
     }
     case MAT_METAL: {  // material.hpp:86-106
       float3 refl = fma3(-2.0f * dot(d_in, s.n), s.n, d_in);
-      d_out = fma3(m0.w, unit_vector_from(u01(rnd.x), u01(rnd.y)), normalize3(refl));
+      d_out = fma3(m0.w, rv, normalize3(refl));
       atten = xyz(m0);
       return dot(d_out, s.n) > 0.0f;
     }
@@ -553,11 +567,11 @@ __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface
       return true;
     }
     case MAT_LIGHT:  // material.hpp:223-240: emits on both faces, never scatters
-      emit = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
+      emit = tv;
       return false;
     default:  // MAT_ISOTROPIC, SURVEY B.3
-      d_out = unit_vector_from(u01(rnd.x), u01(rnd.y));
-      atten = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
+      d_out = rv;
+      atten = tv;
       return true;
   }
 }
