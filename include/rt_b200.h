@@ -207,7 +207,10 @@ typedef struct rt_render_opts {
 
 enum {
   RT_RENDER_DEFAULT = 0,
-  RT_RENDER_COUNTERS = 1 /* instrumented kernel: also fills rt_stats.census (slower; not for timing) */
+  RT_RENDER_COUNTERS = 1,  /* instrumented kernel: also fills rt_stats.census (slower; not for timing) */
+  RT_RENDER_MEGAKERNEL = 2, /* force the one-path-per-lane megakernel (render_kernel)               */
+  RT_RENDER_POOL = 4        /* force the per-warp path-pool kernel (pool_kernel); with neither bit the
+                               library picks (env RT_B200_KERNEL=mega|pool overrides the default)   */
 };
 
 /* Asynchronous on the context's stream.  Accumulates fixed-point (2^-32) int64 RGB

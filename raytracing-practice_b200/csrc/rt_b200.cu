@@ -50,6 +50,10 @@ struct RenderParams {
 #define RT_THREADS 1024
 #endif
 constexpr int kRenderThreads = RT_THREADS;
+#ifndef RT_DEFAULT_POOL
+#define RT_DEFAULT_POOL 0
+#endif
+constexpr bool kDefaultPoolKernel = RT_DEFAULT_POOL != 0;
 constexpr float kFixScale = 4294967296.0f;  // 2^32
 
 __device__ __forceinline__ long long to_fixed(float v) {
@@ -187,6 +191,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     for (int i = 0; i < CN_COUNT; i++)
       if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);
 }
+
+}  // namespace rtb200
+#include "rt_pool.cuh"
+namespace rtb200 {
 
 // ---- write_color (common/color.hpp:26-58) on the device, in double like the reference ----
 __global__ void finalize_kernel(const long long* __restrict__ accum, long long n_values, double scale, float* __restrict__ radiance,
@@ -744,16 +752,46 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   P.smem_nodes = ctx->smem_nodes;
   size_t smem = size_t(P.smem_nodes) * 64;
   const bool count = (opts->flags & RT_RENDER_COUNTERS) != 0;
-  RT_CUDA(ctx, cudaFuncSetAttribute(count ? render_kernel<true> : render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  // counters[0] = first item not pre-assigned to a thread
-  unsigned long long first = (unsigned long long)threads;
-  RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+  // kernel choice: the per-warp path-pool kernel (rt_pool.cuh) unless the megakernel is asked for
+  bool pool = kDefaultPoolKernel;
+  if (const char* e = std::getenv("RT_B200_KERNEL")) pool = std::string(e) == "pool" ? true : (std::string(e) == "mega" ? false : pool);
+  if (opts->flags & RT_RENDER_MEGAKERNEL) pool = false;
+  if (opts->flags & RT_RENDER_POOL) pool = true;
   RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  if (count)
-    render_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
-  else
-    render_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
-  ctx->launches++;
+  if (P.cam.max_depth <= 0) {
+    // ray_color returns black at once (camera.hpp:183-186): nothing to trace, the sums stay as they are
+  } else if (pool) {
+    // work items of a power-of-two number of samples (the kernel finds the end of an item with a mask)
+    int c2 = 1;
+    while (c2 * 2 <= P.chunk) c2 *= 2;
+    P.chunk = c2;
+    P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
+    const unsigned long long items = (unsigned long long)P.per_chunk * (unsigned long long)P.n_chunks;
+    if (items >= 0xFFFFFFFFull) return fail(ctx, RT_ERR_INVALID, "image x samples too large for one launch: shard the samples");
+    P.n_items = unsigned(items);
+    const size_t pool_bytes = pool_smem_bytes(kRenderThreads);
+    if (ctx->smem_optin < pool_bytes + 1024) return fail(ctx, RT_ERR_UNSUPPORTED, "not enough shared memory for the path pools");
+    P.smem_nodes = int(std::min<size_t>(size_t(ctx->sc.n_nodes), (ctx->smem_optin - 1024 - pool_bytes) / 64));
+    smem = size_t(P.smem_nodes) * 64 + pool_bytes;
+    const unsigned long long zero = 0ull;  // items are handed out from 0
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaFuncSetAttribute(count ? pool_kernel<true> : pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (count)
+      pool_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    else
+      pool_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+  } else {
+    RT_CUDA(ctx, cudaFuncSetAttribute(count ? render_kernel<true> : render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // counters[0] = first item not pre-assigned to a thread
+    unsigned long long first = (unsigned long long)threads;
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+    if (count)
+      render_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    else
+      render_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+  }
   ctx->samples_total += (unsigned long long)f.image_width * f.image_height * P.sample_count;
   RT_CUDA(ctx, cudaGetLastError());
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
