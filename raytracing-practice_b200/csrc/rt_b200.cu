@@ -44,6 +44,7 @@ struct RenderParams {
   unsigned long long* accum;     // 3 x int64 per pixel (two's complement adds)
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
+  float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
 };
 
 #ifndef RT_THREADS
@@ -54,6 +55,10 @@ constexpr int kRenderThreads = RT_THREADS;
 #define RT_DEFAULT_POOL 0
 #endif
 constexpr bool kDefaultPoolKernel = RT_DEFAULT_POOL != 0;
+#ifndef RT_POOL_SMEM_NODES
+#define RT_POOL_SMEM_NODES 256
+#endif
+constexpr int kPoolSmemNodes = RT_POOL_SMEM_NODES;
 constexpr float kFixScale = 4294967296.0f;  // 2^32
 
 __device__ __forceinline__ long long to_fixed(float v) {
@@ -434,6 +439,7 @@ struct rt_ctx {
   unsigned long long rays_total = 0, samples_total = 0;
   int smem_nodes = 0;
   int launches = 0;
+  void* pool_cold = nullptr;  // pool kernel, RT_POOL_COLD_GLOBAL builds only
 };
 
 #define RT_CUDA(ctx, call)                                                                          \
@@ -613,6 +619,7 @@ void rt_shutdown(rt_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_scene(ctx);
   cudaFree(ctx->accum);
+  cudaFree(ctx->pool_cold);
   cudaFree(ctx->counters);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -770,9 +777,14 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
     if (items >= 0xFFFFFFFFull) return fail(ctx, RT_ERR_INVALID, "image x samples too large for one launch: shard the samples");
     P.n_items = unsigned(items);
     const size_t pool_bytes = pool_smem_bytes(kRenderThreads);
-    if (ctx->smem_optin < pool_bytes + 1024) return fail(ctx, RT_ERR_UNSUPPORTED, "not enough shared memory for the path pools");
-    P.smem_nodes = int(std::min<size_t>(size_t(ctx->sc.n_nodes), (ctx->smem_optin - 1024 - pool_bytes) / 64));
+    if (ctx->smem_optin < pool_bytes + 4096) return fail(ctx, RT_ERR_UNSUPPORTED, "not enough shared memory for the path pools");
+    // only the very top of the BVH is staged: the pools want the shared memory, and L1 (what is left of the
+    // 256 KB) holds the hot nodes just as well — measured, gpurun_out/ab_smem_nodes.log
+    P.smem_nodes = int(std::min<size_t>({size_t(ctx->sc.n_nodes), size_t(kPoolSmemNodes), (ctx->smem_optin - 2048 - pool_bytes) / 64}));
+    if (const char* e = std::getenv("RT_B200_SMEM_NODES")) P.smem_nodes = std::min(P.smem_nodes, std::max(0, std::atoi(e)));  // experiments: L1 vs shared
     smem = size_t(P.smem_nodes) * 64 + pool_bytes;
+    if (pool_cold_global_bytes(grid, kRenderThreads) && !ctx->pool_cold) RT_CUDA(ctx, cudaMalloc(&ctx->pool_cold, pool_cold_global_bytes(grid, kRenderThreads)));
+    P.pool_cold = static_cast<float*>(ctx->pool_cold);
     const unsigned long long zero = 0ull;  // items are handed out from 0
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, cudaFuncSetAttribute(count ? pool_kernel<true> : pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -202,7 +202,19 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
   return t2 != INF;
 }
 
-__device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float tmin, float tmax, float u) {
+// Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2)
+// of the ray's (pixel, sample, bounce) counter.
+__device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bounce, int medium) {
+  uint4 r = rng_block(key, bounce, 1u + (uint32_t(medium) >> 2));
+  uint32_t c = uint32_t(medium) & 3u;
+  return u01(c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w)));
+}
+
+// The free-flight uniform is drawn LAZILY, only once the ray is known to cross the medium inside
+// [tmin, tmax]: most BVH-leaf visits of a medium's bounding box miss the boundary itself, and the
+// Philox block was 2/3 of this function's instructions (profiles/r06_pool_first.md).
+__device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& m, int mi, float3 o, float3 d, float time, float tmin, float tmax,
+                                          const PathKey& key, uint32_t bounce) {
   float t1, t2;
   if (!medium_span(sc, m, o, d, time, t1, t2)) return -1.0f;
   t1 = fmaxf(t1, tmin);
@@ -211,17 +223,10 @@ __device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& 
   t1 = fmaxf(t1, 0.0f);
   float len = sqrtf(dot(d, d));
   float inside = (t2 - t1) * len;
+  const float u = medium_uniform(key, bounce, mi);
   float hit_distance = m.neg_inv_density * __logf(u);  // u == 0 -> +inf -> miss, as log(0) in the reference
   if (!(hit_distance <= inside)) return -1.0f;
   return t1 + hit_distance / len;
-}
-
-// Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2)
-// of the ray's (pixel, sample, bounce) counter.
-__device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bounce, int medium) {
-  uint4 r = rng_block(key, bounce, 1u + (uint32_t(medium) >> 2));
-  uint32_t c = uint32_t(medium) & 3u;
-  return u01(c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w)));
 }
 
 constexpr int kStackDepth = 32;
@@ -283,7 +288,7 @@ __device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, 
     for (int g = 0; g < sc.n_global_media; g++) {
       const int mi = sc.global_media[g];
       const DMedium m = sc.media[mi];
-      float t = medium_sample(sc, m, o, d, time, tmin, ts.best.t, medium_uniform(key, bounce, mi));
+      float t = medium_sample(sc, m, mi, o, d, time, tmin, ts.best.t, key, bounce);
       if (COUNT) cn[CN_MEDIUM]++;
       if (t != -1.0f) ts.best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
     }
@@ -330,8 +335,9 @@ __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const Nod
 }
 
 // leaf: ~cur = (first << 3) | (count - 1)
-template <bool COUNT>
-__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn) {
+// `key_of(key, bounce)` yields the ray's Philox counter; it is only called when a medium is actually sampled
+template <bool COUNT, typename KeyFn>
+__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn) {
   const int code = ~ts.cur;
   const int first = code >> 3, count = (code & 7) + 1;
   const float3 o = ts.o, d = ts.d;
@@ -353,7 +359,10 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
       }
     } else if (ref != REF_NONE && media) {
       const DMedium m = sc.media[idx];
-      t = medium_sample(sc, m, o, d, ts.time, ts.tmin, ts.best.t, medium_uniform(key, bounce, int(idx)));
+      PathKey key;
+      uint32_t bounce;
+      key_of(key, bounce);
+      t = medium_sample(sc, m, int(idx), o, d, ts.time, ts.tmin, ts.best.t, key, bounce);
       if (COUNT) cn[CN_MEDIUM]++;
     }
     if (t != -1.0f) ts.best = Hit{t, ref};
@@ -383,7 +392,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
     if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
       if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
     } else {
-      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, key, bounce, cn);
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
     }
   }
   return ts.best;
