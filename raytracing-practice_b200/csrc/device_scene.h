@@ -37,7 +37,7 @@ inline
 
 // child encoding inside a node: >= 0 internal node index; < 0 leaf: ~((first << 3) | (count-1))
 // an EMPTY child has an inverted box (min=+inf, max=-inf) and is never entered.
-constexpr int kMaxLeaf = 4;
+constexpr int kMaxLeaf = 6;  // <= 8 (3 bits in the leaf code)
 
 struct DMedium {
   float neg_inv_density;
@@ -89,6 +89,7 @@ struct DeviceScene {
   int n_global_media;   // media that enclose the whole scene: sampled once per ray, not via the BVH
   int global_media[4];
   float scene_abs_max;  // max |coordinate| of any finite bound (conservative-cull epsilon scale)
+  float bounds_lo[3], bounds_hi[3];  // union of every BVH item's box (= what node 0 covers); empty scene: +inf / -inf
 };
 
 }  // namespace rtb200

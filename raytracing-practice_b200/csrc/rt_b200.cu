@@ -677,6 +677,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.n_materials = int(h.materials.size() / 2);
   s.n_textures = int(h.textures.size() / 2);
   s.scene_abs_max = h.scene_abs_max;
+  for (int a = 0; a < 3; a++) s.bounds_lo[a] = h.bounds_lo[a], s.bounds_hi[a] = h.bounds_hi[a];
   s.n_global_media = int(h.global_media.size());
   for (int i = 0; i < 4; i++) s.global_media[i] = i < s.n_global_media ? h.global_media[size_t(i)] : -1;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

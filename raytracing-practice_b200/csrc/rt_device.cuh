@@ -168,6 +168,18 @@ __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4&
 // then an exponential free-flight sample.  `u` is the uniform this medium owns for this ray.
 __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float& t1, float& t2) {
   const float INF = __int_as_float(0x7f800000);
+  if (m.n_bref == 1) {  // a single sphere (the usual boundary): both passes below come from ONE pair of roots
+    const uint32_t ref = __ldg(sc.medium_brefs + m.first_bref);
+    if ((ref >> 30) == REF_SPHERE) {
+      const uint32_t idx = ref & 0x3FFFFFFFu;
+      float r0, r1;
+      t1 = INF;
+      if (!sphere_roots(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, r0, r1)) return false;
+      t1 = r0;                                // pass 1: the smallest crossing
+      t2 = r1 > t1 + 0.0001f ? r1 : INF;      // pass 2: the next crossing beyond t1 + 0.0001 (r0 itself never is)
+      return t2 != INF;
+    }
+  }
   t1 = INF;
   // pass 1: boundary->hit(r, universe): the smallest crossing
   for (int k = 0; k < m.n_bref; k++) {
@@ -273,26 +285,49 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
   return MODE_SHADE;  // traversal finished: ts.best is the answer
 }
 
-// Start a query.  `media`: sample the scene-enclosing media (met by every ray — the r=5000 fog of
-// the Book-2 final scene) right here, where the caller's lanes are converged, not as a BVH leaf.
-template <bool COUNT>
-__device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, float3 o, float3 d, float time, float tmin, float tmax, uint32_t skip,
-                                          bool media, const PathKey& key, uint32_t bounce, unsigned int* cn) {
+// 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
+__device__ __forceinline__ void trav_set_ray(TravState& ts, float3 o, float3 d, float time, float tmin, uint32_t skip) {
   ts.o = o, ts.d = d, ts.time = time, ts.tmin = tmin, ts.skip = skip;
-  // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
   ts.inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
               fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
   ts.ood = o * ts.inv;
-  ts.best = Hit{tmax, REF_NONE};
-  if (media) {
-    for (int g = 0; g < sc.n_global_media; g++) {
-      const int mi = sc.global_media[g];
-      const DMedium m = sc.media[mi];
-      float t = medium_sample(sc, m, mi, o, d, time, tmin, ts.best.t, key, bounce);
-      if (COUNT) cn[CN_MEDIUM]++;
-      if (t != -1.0f) ts.best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
-    }
+}
+
+// The scene-enclosing media (met by every ray — the r=5000 fog of the Book-2 final scene) are not BVH leaves:
+// they are sampled once per ray, where the caller's lanes are converged; the result seeds the closest hit.
+template <bool COUNT>
+__device__ __forceinline__ Hit sample_global_media(const DeviceScene& sc, float3 o, float3 d, float time, float tmin, float tmax, const PathKey& key,
+                                                   uint32_t bounce, unsigned int* cn) {
+  Hit best{tmax, REF_NONE};
+  for (int g = 0; g < sc.n_global_media; g++) {
+    const int mi = sc.global_media[g];
+    const DMedium m = sc.media[mi];
+    float t = medium_sample(sc, m, mi, o, d, time, tmin, best.t, key, bounce);
+    if (COUNT) cn[CN_MEDIUM]++;
+    if (t != -1.0f) best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
   }
+  return best;
+}
+
+// Does the ray cross the box of everything the BVH holds inside (tmin, tmax)?  Same arithmetic as node_step on
+// boxes that are subsets of this one, and fma / min / max are monotone, so a miss here implies a miss at every
+// node: skipping the traversal for such rays cannot change any result.
+__device__ __forceinline__ bool ray_meets_scene(const DeviceScene& sc, const TravState& ts, float tmax) {
+  const float x0 = fmaf(sc.bounds_lo[0], ts.inv.x, -ts.ood.x), x1 = fmaf(sc.bounds_hi[0], ts.inv.x, -ts.ood.x);
+  const float y0 = fmaf(sc.bounds_lo[1], ts.inv.y, -ts.ood.y), y1 = fmaf(sc.bounds_hi[1], ts.inv.y, -ts.ood.y);
+  const float z0 = fmaf(sc.bounds_lo[2], ts.inv.z, -ts.ood.z), z1 = fmaf(sc.bounds_hi[2], ts.inv.z, -ts.ood.z);
+  const float n = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+  const float f = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+  return n <= f;
+}
+
+// Start a query.  `media`: sample the scene-enclosing media right here.
+template <bool COUNT>
+__device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, float3 o, float3 d, float time, float tmin, float tmax, uint32_t skip,
+                                          bool media, const PathKey& key, uint32_t bounce, unsigned int* cn) {
+  trav_set_ray(ts, o, d, time, tmin, skip);
+  ts.best = Hit{tmax, REF_NONE};
+  if (media) ts.best = sample_global_media<COUNT>(sc, o, d, time, tmin, tmax, key, bounce, cn);
   ts.sp = 0;
   ts.cur = 0;
   return MODE_NODE;
@@ -375,6 +410,26 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
 // warp votes with the full mask, which force reconvergence every iteration; MUST be called with
 // the warp converged (exited lanes excepted).  With plain per-lane `continue`s the compiler never
 // re-merged the lanes: ncu showed 4.75 of 32 active per instruction (profiles/r01_*.md).
+// `ts` holds a ray (trav_set_ray) and its closest hit so far (ts.best); lanes with active == false only vote
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const NodeSource& ns, TravState& ts, bool media, const PathKey& key,
+                                                    uint32_t bounce, unsigned int* cn, bool active) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  TravStack st;
+  int mode = MODE_DONE;
+  if (active) ts.sp = 0, ts.cur = 0, mode = MODE_NODE;
+  for (;;) {
+    const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF);
+    if ((bN | bL) == 0u) break;
+    if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
+      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    } else {
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+    }
+  }
+  return ts.best;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
                                            uint32_t skip_ref, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn, bool active = true) {

@@ -32,6 +32,12 @@ namespace rtb200 {
 #define RT_POOL_REFILL 12  // refill idle trace lanes once at least this many are idle
 #endif
 
+#ifndef RT_POOL_SHADE_MISSES
+#define RT_POOL_SHADE_MISSES 0  // 1: SHADE finishes rays that miss the scene's bounding box itself (measured: -28 %, a divergent loop)
+#endif
+#ifndef RT_POOL_NODE_LOOP
+#define RT_POOL_NODE_LOOP 1  // TRACE keeps taking node steps while NODE lanes stay the majority (1 vote per step)
+#endif
 #ifndef RT_POOL_COLD_GLOBAL
 #define RT_POOL_COLD_GLOBAL 0  // 1: the shade-only words of a path live in global memory (L1/L2), not shared
 #endif
@@ -59,7 +65,7 @@ constexpr size_t pool_cold_global_bytes(int ctas, int threads) { return RT_POOL_
 // copy of the launch parameters, because an outlined function cannot address the kernel's constant bank.
 template <bool COUNT>
 __device__ __noinline__ int shade_slot(const RenderParams* __restrict__ Pp, float* __restrict__ pool, float* __restrict__ cold, unsigned slot,
-                                       unsigned int* cn) {
+                                       unsigned int& rays_here, unsigned int* cn) {
   constexpr int NP = RT_POOL_NP;
   const RenderParams& P = *Pp;
   const DeviceScene& sc = P.sc;
@@ -68,17 +74,23 @@ __device__ __noinline__ int shade_slot(const RenderParams* __restrict__ Pp, floa
   float3 o, d, beta;
   float time;
   uint32_t skip;
-  bool regen = true;
-  if (depth > 0) {
+  // radiance of a path = beta * (emission | background) at its LAST vertex: no material here both emits and
+  // scatters (diffuse_light::scatter is false, material.hpp:36), so no running sum is kept in the pool
+  auto deposit = [&](float3 L) {  // the finished sample, quantised to 2^-32, straight into the int64 accumulator
+    unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
+    const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
+    if (fr) atomicAdd(dst + 0, (unsigned long long)fr);
+    if (fg) atomicAdd(dst + 1, (unsigned long long)fg);
+    if (fb) atomicAdd(dst + 2, (unsigned long long)fb);
+  };
+  bool alive = false;
+  if (depth > 0) {  // ---- the tail of one ray_color level (camera.hpp:192-231) for the query TRACE finished ----
     o = f3(PF(PF_OX, slot), PF(PF_OY, slot), PF(PF_OZ, slot));
     d = f3(PF(PF_DX, slot), PF(PF_DY, slot), PF(PF_DZ, slot));
     time = PF(PF_TIME, slot);
     beta = f3(CF(PC_BX, slot), CF(PC_BY, slot), CF(PC_BZ, slot));
     const Hit h{PF(PF_HT, slot), (uint32_t)PI(PF_HREF, slot)};
-    // radiance of a path = beta * (emission | background) at its LAST vertex: no material here both
-    // emits and scatters (diffuse_light::scatter is false, material.hpp:36), so no running sum is kept
     float3 L = f3(0.0f, 0.0f, 0.0f);
-    bool alive = false;
     if (h.ref == REF_NONE) {
       L = L + beta * P.cam.bg;
     } else {
@@ -97,81 +109,98 @@ __device__ __noinline__ int shade_slot(const RenderParams* __restrict__ Pp, floa
         alive = --depth > 0;
       }
     }
-    if (!alive) {
-      // the finished sample, quantised to 2^-32, straight into the int64 accumulator (red.add.u64)
-      unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
-      const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
-      if (fr) atomicAdd(dst + 0, (unsigned long long)fr);
-      if (fg) atomicAdd(dst + 1, (unsigned long long)fg);
-      if (fb) atomicAdd(dst + 2, (unsigned long long)fb);
-    } else {
-      regen = false;
-    }
+    if (!alive) deposit(L);
   }
-  if (regen) {  // ---- next sample of this slot's work item, or the next item ----
-    const int s_last = P.sample_begin + P.sample_count;
-    int s_next = smp + 1;
-    bool have = pixel >= 0 && ((s_next - P.sample_begin) & (P.chunk - 1)) != 0 && s_next < s_last;
-    if (!have) {
-      for (;;) {
-        const unsigned long long it = atomicAdd(P.counters, 1ull);
-        if (it >= (unsigned long long)P.n_items) break;
-        const unsigned int item = (unsigned int)it;
-        const unsigned int chunk = item / P.per_chunk, q = item - chunk * P.per_chunk;
-        const unsigned int tile = q >> 5, l = q & 31u;
-        const int px = int(tile % (unsigned)P.tiles_x) * 8 + int(l & 7u);
-        const int py = int(tile / (unsigned)P.tiles_x) * 4 + int(l >> 3);
-        s_next = P.sample_begin + int(chunk) * P.chunk;
-        if (px < P.cam.W && py < P.cam.H && s_next < s_last) {
-          pixel = py * P.cam.W + px;
-          have = true;
-          break;
+  // ---- until this slot holds a ray that needs the BVH (or the image has no samples left for it) ----
+  Hit best;
+#pragma unroll 1
+  for (;;) {
+    if (!alive) {  // next sample of this slot's work item, or the next item
+      const int s_last = P.sample_begin + P.sample_count;
+      int s_next = smp + 1;
+      bool have = pixel >= 0 && ((s_next - P.sample_begin) & (P.chunk - 1)) != 0 && s_next < s_last;
+      if (!have) {
+        for (;;) {
+          const unsigned long long it = atomicAdd(P.counters, 1ull);
+          if (it >= (unsigned long long)P.n_items) break;
+          const unsigned int item = (unsigned int)it;
+          const unsigned int chunk = item / P.per_chunk, q = item - chunk * P.per_chunk;
+          const unsigned int tile = q >> 5, l = q & 31u;
+          const int px = int(tile % (unsigned)P.tiles_x) * 8 + int(l & 7u);
+          const int py = int(tile / (unsigned)P.tiles_x) * 4 + int(l >> 3);
+          s_next = P.sample_begin + int(chunk) * P.chunk;
+          if (px < P.cam.W && py < P.cam.H && s_next < s_last) {
+            pixel = py * P.cam.W + px;
+            have = true;
+            break;
+          }
         }
       }
+      if (!have) {
+        CI(PC_DEPTH, slot) = 0;
+        return 0;
+      }
+      // camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time
+      smp = s_next;
+      const PathKey key{P.key, (uint32_t)pixel, (uint32_t)smp};
+      const int py = pixel / P.cam.W, px = pixel - py * P.cam.W;
+      const uint4 r0 = rng_block(key, 0u, 0u);
+      const float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
+      time = u01(r0.z);
+      float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
+      o = P.cam.center;
+      if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
+        const uint4 r1 = rng_block(key, 0u, 1u);
+        float rr = sqrtf(u01(r1.x)), sn, cs;
+        sincospif(2.0f * u01(r1.y), &sn, &cs);
+        const float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
+        o = o + off;
+        dir = dir - off;
+      }
+      d = dir;
+      beta = f3(1.0f, 1.0f, 1.0f);
+      depth = P.cam.max_depth;
+      skip = REF_NONE;
+      alive = true;
     }
-    if (!have) {
-      CI(PC_DEPTH, slot) = 0;
-      return 0;
-    }
-    // camera::get_ray (camera.hpp:139-162): jitter, defocus disk, shutter time
-    smp = s_next;
-    const PathKey key{P.key, (uint32_t)pixel, (uint32_t)smp};
-    const int py = pixel / P.cam.W, px = pixel - py * P.cam.W;
-    const uint4 r0 = rng_block(key, 0u, 0u);
-    const float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
-    time = u01(r0.z);
-    float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
-    o = P.cam.center;
-    if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
-      const uint4 r1 = rng_block(key, 0u, 1u);
-      float rr = sqrtf(u01(r1.x)), sn, cs;
-      sincospif(2.0f * u01(r1.y), &sn, &cs);
-      const float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
-      o = o + off;
-      dir = dir - off;
-    }
-    d = dir;
-    beta = f3(1.0f, 1.0f, 1.0f);
-    depth = P.cam.max_depth;
-    skip = REF_NONE;
-    CI(PC_PIXEL, slot) = pixel;
-    CI(PC_SAMPLE, slot) = smp;
-    PF(PF_TIME, slot) = time;
-  }
-  // the scene-enclosing media (met by every ray: the r=5000 fog of the Book-2 final scene) are sampled
-  // here, for the NEXT query, while the warp is converged; the result seeds the traversal's closest hit
-  Hit best{INF, REF_NONE};
-  if (sc.n_global_media) {
+    // world.hit, part 1: the scene-enclosing media (met by every ray: the r=5000 fog of the Book-2 final scene)
+    // are sampled here, for the NEXT query, while the warp is converged; the result seeds the closest hit
     const PathKey key{P.key, (uint32_t)pixel, (uint32_t)smp};
     const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;
-    for (int g = 0; g < sc.n_global_media; g++) {
-      const int mi = sc.global_media[g];
-      const DMedium m = sc.media[mi];
-      const float t = medium_sample(sc, m, mi, o, d, time, 0.001f, best.t, key, bounce);
-      if (COUNT) cn[CN_MEDIUM]++;
-      if (t != -1.0f) best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
+    best = Hit{INF, REF_NONE};
+    if (sc.n_global_media) best = sample_global_media<COUNT>(sc, o, d, time, 0.001f, INF, key, bounce, cn);
+#if RT_POOL_SHADE_MISSES
+    // ... and a ray that misses the box of all geometry (or is stopped by the medium first) needs no BVH at
+    // all: finish it here, where the cost of doing so is shared by the 32 lanes of the SHADE round
+    TravState ts;
+    trav_set_ray(ts, o, d, time, 0.001f, skip);
+    if (ray_meets_scene(sc, ts, best.t)) break;
+    if (best.ref == REF_NONE) {
+      rays_here++;
+      deposit(beta * P.cam.bg);
+      alive = false;
+    } else {
+      const int mat = sc.media[best.ref & 0x3FFFFFFFu].material;
+      const float4 m1 = __ldg(sc.materials + 2 * mat + 1);
+      if (__float_as_int(m1.x) != MAT_ISOTROPIC) break;  // not a phase function this shortcut knows: general path
+      rays_here++;
+      if (COUNT) cn[CN_ISO]++;
+      const uint4 rnd = rng_block(key, bounce, 0u);
+      const float3 p = fma3(best.t, d, o);
+      const float3 tv = texture_value<COUNT>(sc, __float_as_int(m1.y), 0.0f, 0.0f, p, cn);
+      beta = beta * tv;  // isotropic::scatter: attenuation = texture, direction uniform on the sphere
+      o = p;
+      d = unit_vector_from(u01(rnd.x), u01(rnd.y));
+      skip = REF_NONE;
+      alive = --depth > 0;  // a path cut by max_depth contributes black: nothing to deposit
     }
+#else
+    break;
+#endif
   }
+  CI(PC_PIXEL, slot) = pixel;
+  CI(PC_SAMPLE, slot) = smp;
+  PF(PF_TIME, slot) = time;
   PF(PF_OX, slot) = o.x, PF(PF_OY, slot) = o.y, PF(PF_OZ, slot) = o.z;
   PF(PF_DX, slot) = d.x, PF(PF_DY, slot) = d.y, PF(PF_DZ, slot) = d.z;
   PI(PF_SKIP, slot) = (int)skip;
@@ -205,6 +234,7 @@ __device__ __noinline__ bool shade_phase(const RenderParams* __restrict__ Pp, fl
   unsigned int* const qc = reinterpret_cast<unsigned int*>(pool + kPoolCtlOff);
   unsigned tq_head = qc[QC_TQ_HEAD], tq_n = qc[QC_TQ_N], sq_head = qc[QC_SQ_HEAD], sq_n = qc[QC_SQ_N], n_dead = qc[QC_DEAD];
   const unsigned n_busy = qc[QC_BUSY];
+  unsigned int rays_here = 0;
   __syncwarp();
   while (sq_n >= 32u || (sq_n > 0u && tq_n < 32u - n_busy)) {
     const unsigned take = min(sq_n, 32u);
@@ -212,7 +242,7 @@ __device__ __noinline__ bool shade_phase(const RenderParams* __restrict__ Pp, fl
     unsigned slot = 0;
     if (lane < take) {
       slot = sq[(sq_head + lane) & QM];
-      has_ray = shade_slot<COUNT>(Pp, pool, cold, slot, cn);
+      has_ray = shade_slot<COUNT>(Pp, pool, cold, slot, rays_here, cn);
     }
     sq_head = (sq_head + take) & QM;
     sq_n -= take;
@@ -221,7 +251,8 @@ __device__ __noinline__ bool shade_phase(const RenderParams* __restrict__ Pp, fl
     tq_n += __popc(bR);
     n_dead += __popc(__ballot_sync(FULL, has_ray == 0));
   }
-  if (lane == 0) qc[QC_TQ_HEAD] = tq_head, qc[QC_TQ_N] = tq_n, qc[QC_SQ_HEAD] = sq_head, qc[QC_SQ_N] = sq_n, qc[QC_DEAD] = n_dead;
+  rays_here = __reduce_add_sync(FULL, rays_here);
+  if (lane == 0) qc[QC_TQ_HEAD] = tq_head, qc[QC_TQ_N] = tq_n, qc[QC_SQ_HEAD] = sq_head, qc[QC_SQ_N] = sq_n, qc[QC_DEAD] = n_dead, qc[QC_RAYS] += rays_here;
   __syncwarp();
   return n_dead != NP;
 }
@@ -289,12 +320,24 @@ __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, fl
       if (sq_n > 0u || busy == 0u) break;  // finished queries wait for shading (or nothing is left at all)
     }
     if (__popc(bN) >= __popc(bL)) {
+#if RT_POOL_NODE_LOOP
+      const unsigned thr = max(1u, (n_busy + 1u) >> 1);
+      do {
+        if (mode == MODE_NODE) {
+          const float4 s0 = lsc[0], s1 = lsc[32];
+          ts.inv = f3(s0.x, s0.y, s0.z);
+          ts.ood = f3(s0.w, s1.x, s1.y);
+          mode = node_step<COUNT>(ts, st, ns, cn);
+        }
+      } while ((unsigned)__popc(__ballot_sync(FULL, mode == MODE_NODE)) >= thr);
+#else
       if (mode == MODE_NODE) {
         const float4 s0 = lsc[0], s1 = lsc[32];
         ts.inv = f3(s0.x, s0.y, s0.z);
         ts.ood = f3(s0.w, s1.x, s1.y);
         mode = node_step<COUNT>(ts, st, ns, cn);
       }
+#endif
     } else {
       if (mode == MODE_LEAF) {
         ts.o = f3(PF(PF_OX, tslot), PF(PF_OY, tslot), PF(PF_OZ, tslot));

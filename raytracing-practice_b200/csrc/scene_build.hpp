@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -51,6 +52,8 @@ struct HostScene {
   std::vector<int2> xchains;
   std::vector<int> global_media;  // media enclosing every other item (at most 4)
   float scene_abs_max = 1.0f;
+  float bounds_lo[3] = {std::numeric_limits<float>::infinity(), std::numeric_limits<float>::infinity(), std::numeric_limits<float>::infinity()};
+  float bounds_hi[3] = {-std::numeric_limits<float>::infinity(), -std::numeric_limits<float>::infinity(), -std::numeric_limits<float>::infinity()};
   int bvh_depth = 0;
   double sah_cost = 0;
   std::string error;
@@ -307,13 +310,20 @@ struct SahBuilder {
   std::vector<Item>& items;
   std::vector<TmpNode> nodes;
   std::vector<Item> ordered;
-  explicit SahBuilder(std::vector<Item>& it) : items(it) {}
+  // SAH constants in units of one node visit (two slab tests).  A leaf primitive costs more than its flop count
+  // says because leaf steps run at low SIMD efficiency; values fitted on the GPU (profiles/r08_sah_constants.md).
+  double prim_scale = 0.5;
+  int max_leaf = kMaxLeaf;
+  explicit SahBuilder(std::vector<Item>& it) : items(it) {
+    if (const char* e = std::getenv("RT_B200_SAH_PRIM")) prim_scale = std::max(0.01, std::atof(e));
+    if (const char* e = std::getenv("RT_B200_MAX_LEAF")) max_leaf = std::min(8, std::max(1, std::atoi(e)));
+  }
 
   int build(int begin, int end) {
     TmpNode n;
     n.box.reset();
     float leaf_cost = 0;
-    for (int i = begin; i < end; i++) n.box.grow(items[size_t(i)].box), leaf_cost += items[size_t(i)].cost;
+    for (int i = begin; i < end; i++) n.box.grow(items[size_t(i)].box), leaf_cost += float(prim_scale) * items[size_t(i)].cost;
     const int count = end - begin;
     int best_axis = -1, best_split = -1;
     double best = std::numeric_limits<double>::infinity();
@@ -330,7 +340,7 @@ struct SahBuilder {
         double c = 0;
         for (int i = count - 1; i > 0; i--) {
           acc.grow(items[size_t(begin + i)].box);
-          c += items[size_t(begin + i)].cost;
+          c += prim_scale * items[size_t(begin + i)].cost;
           right_area[size_t(i)] = acc.area();
           right_cost[size_t(i)] = c;
         }
@@ -338,13 +348,13 @@ struct SahBuilder {
         c = 0;
         for (int i = 1; i < count; i++) {
           acc.grow(items[size_t(begin + i - 1)].box);
-          c += items[size_t(begin + i - 1)].cost;
+          c += prim_scale * items[size_t(begin + i - 1)].cost;
           double sah = 1.0 + (acc.area() * c + right_area[size_t(i)] * right_cost[size_t(i)]) / parent_area;
           if (sah < best) best = sah, best_axis = axis, best_split = i;
         }
       }
     }
-    const bool make_leaf = count <= 1 || (count <= kMaxLeaf && double(leaf_cost) <= best);
+    const bool make_leaf = count <= 1 || (count <= max_leaf && double(leaf_cost) <= best);
     if (make_leaf) {
       n.first = int(ordered.size());
       n.count = count;
@@ -493,6 +503,8 @@ inline bool build_host_scene(const rt_scene_desc* d, HostScene& out) {
       if (std::isfinite(it.box.hi[a])) amax = std::max(amax, std::fabs(it.box.hi[a]));
     }
   out.scene_abs_max = amax;
+  for (const Item& it : b.items)
+    for (int a = 0; a < 3; a++) out.bounds_lo[a] = std::min(out.bounds_lo[a], it.box.lo[a]), out.bounds_hi[a] = std::max(out.bounds_hi[a], it.box.hi[a]);
 
   // ---- BVH ----------------------------------------------------------------------------
   Box empty;
