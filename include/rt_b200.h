@@ -244,16 +244,18 @@ typedef struct rt_stats {
   int32_t image_height;
   int32_t n_nodes; /* device BVH                                                       */
   int32_t n_spheres;
-  int32_t n_quads;
+  int32_t n_quads; /* quad records, including the six behind every box                 */
   int32_t n_media;
   int32_t bvh_nodes_in_smem;
   int32_t kernel_launches; /* number of kernels this context has launched              */
+  int32_t n_boxes;         /* box() lists turned into one slab-test primitive each     */
+  int32_t reserved0;
   /* RT_RENDER_COUNTERS only, since the last clear — the N_* of the roofline model:
    * [0] BVH node visits (2 box tests each) [1] sphere tests [2] sphere hits [3] quad tests
    * [4] quad tests past the plane/t early-outs [5] medium tests [6..10] scatters by material
    * (lambertian, metal, dielectric, diffuse_light, isotropic) [11] checker [12] image
-   * [13] noise texture evaluations                                                      */
-  uint64_t census[14];
+   * [13] noise texture evaluations [14] box tests                                       */
+  uint64_t census[16];
 } rt_stats;
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 

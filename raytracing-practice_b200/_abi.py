@@ -148,7 +148,9 @@ class rt_stats(C.Structure):
         ("n_media", C.c_int32),
         ("bvh_nodes_in_smem", C.c_int32),
         ("kernel_launches", C.c_int32),
-        ("census", C.c_uint64 * 14),
+        ("n_boxes", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("census", C.c_uint64 * 16),
     ]
 
 

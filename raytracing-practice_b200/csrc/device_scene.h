@@ -7,6 +7,9 @@
 //   leaf_refs  : uint32 per leaf slot: (type << 30) | index,  type 0 sphere / 1 quad / 2 medium
 //   spheres    : 2 x float4 {cx,cy,cz,r} {dcx,dcy,dcz,-}           (world space, baked)
 //   quads      : 3 x float4 {n,D} {A,a0} {B,b0}: t=(D-n.o)/(n.d), alpha=A.p+a0, beta=B.p+b0
+//   boxes      : 3 x float4 {lo,cos} {hi,sin} {t,flag}: the six quads of box() (quad.hpp:129-159) as ONE slab-test
+//                primitive in the box's own frame (a translate/rotate_y instance is one 2x2 rotation of the ray);
+//                box_meta {material, first quad, face map, -}: face -> which of its quad records (uv, id) it is
 //   materials  : 2 x float4; textures: 2 x float4; texels RGBA8; perlin tables float4[256]+perm
 // The fp64 "exact" arrays (X*) keep the reference's OBJECT-space doubles and the instance
 // transform chain, so the parity harness can re-evaluate a candidate exactly as
@@ -28,7 +31,8 @@ struct uchar4 { unsigned char x, y, z, w; };
 
 namespace rtb200 {
 
-enum : uint32_t { REF_SPHERE = 0u, REF_QUAD = 1u, REF_MEDIUM = 2u, REF_NONE = 0xFFFFFFFFu };
+// a box reference carries (box index << 3) | face in its 30 index bits; face = axis * 2 + (hi side), 7 = "the box"
+enum : uint32_t { REF_SPHERE = 0u, REF_QUAD = 1u, REF_MEDIUM = 2u, REF_BOX = 3u, REF_NONE = 0xFFFFFFFFu };
 inline
 #ifdef __CUDACC__
     __host__ __device__
@@ -72,6 +76,8 @@ struct DeviceScene {
   const int2* sph_meta;  // {material, rotation index or -1}
   const float4* quads;
   const int* quad_mat;
+  const float4* boxes;
+  const int4* box_meta;  // {material, first quad record, face map: 4 bits per face = quad offset | inward-normal << 3, 0}
   const DMedium* media;
   const uint32_t* medium_brefs;
   const float4* materials;
@@ -85,7 +91,7 @@ struct DeviceScene {
   const XQuad* xquads;
   const XOp* xops;
   const int2* xchains;  // {first op, n ops}
-  int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures;
+  int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures, n_boxes;
   int n_global_media;   // media that enclose the whole scene: sampled once per ray, not via the BVH
   int global_media[4];
   float scene_abs_max;  // max |coordinate| of any finite bound (conservative-cull epsilon scale)

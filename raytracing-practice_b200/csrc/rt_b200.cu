@@ -280,28 +280,33 @@ __device__ void exact_closest(const DeviceScene& sc, const NodeSource& ns, const
         uint32_t ref = sc.leaf_refs[first + k];
         uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
         if (ref == REF_NONE || type == REF_MEDIUM) continue;  // media are transparent here
-        XRec rec;
-        int order, pid, is_quad = type == REF_QUAD;
-        bool ok;
-        if (is_quad) {
-          const XQuad& q = sc.xquads[idx];
-          ok = exact_quad(sc, q, r, tmin, tmax, rec);
-          order = q.order, pid = q.pid;
-        } else {
-          const XSphere& q = sc.xspheres[idx];
-          ok = exact_sphere(sc, q, r, tmin, tmax, rec);
-          order = q.order, pid = q.pid;
+        // a box leaf stands for its six quads (quad.hpp:145-155), evaluated one by one like the reference does
+        const int n_sub = type == REF_BOX ? 6 : 1;
+        const int sub0 = type == REF_BOX ? sc.box_meta[idx >> 3].y : int(idx);
+        for (int j = 0; j < n_sub; j++) {
+          XRec rec;
+          int order, pid, is_quad = type != REF_SPHERE;
+          bool ok;
+          if (is_quad) {
+            const XQuad& q = sc.xquads[sub0 + j];
+            ok = exact_quad(sc, q, r, tmin, tmax, rec);
+            order = q.order, pid = q.pid;
+          } else {
+            const XSphere& q = sc.xspheres[idx];
+            ok = exact_sphere(sc, q, r, tmin, tmax, rec);
+            order = q.order, pid = q.pid;
+          }
+          if (!ok) continue;
+          bool take;
+          if (best_order < 0) {
+            take = is_quad ? rec.t.v <= best_t : rec.t.v < best_t;
+          } else if (rec.t.v != best_t) {
+            take = rec.t.v < best_t;
+          } else {  // exact tie: the later visit wins iff it is a quad (contains vs surrounds)
+            take = order > best_order ? is_quad != 0 : best_is_quad == 0;
+          }
+          if (take) best_t = rec.t.v, best_order = order, best_is_quad = is_quad, out_pid = pid, out_rec = rec;
         }
-        if (!ok) continue;
-        bool take;
-        if (best_order < 0) {
-          take = is_quad ? rec.t.v <= best_t : rec.t.v < best_t;
-        } else if (rec.t.v != best_t) {
-          take = rec.t.v < best_t;
-        } else {  // exact tie: the later visit wins iff it is a quad (contains vs surrounds)
-          take = order > best_order ? is_quad != 0 : best_is_quad == 0;
-        }
-        if (take) best_t = rec.t.v, best_order = order, best_is_quad = is_quad, out_pid = pid, out_rec = rec;
       }
     }
     if (sp == 0) return;
@@ -336,7 +341,12 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     if (h.ref != REF_NONE) {
       Surface sf = surface_at(sc, h, o, d, float(tm));
       uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
-      pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
+      if (type == REF_BOX) {
+        const int4 meta = sc.box_meta[idx >> 3];
+        pid = sc.xquads[meta.y + int((uint32_t(meta.z) >> (4u * (idx & 7u))) & 7u)].pid;
+      } else {
+        pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
+      }
       t = h.t, nx = sf.n.x, ny = sf.n.y, nz = sf.n.z, front = sf.front;
     }
   }
@@ -656,6 +666,8 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   UP(sph_meta, h.sph_meta)
   UP(quads, h.quads)
   UP(quad_mat, h.quad_mat)
+  UP(boxes, h.boxes)
+  UP(box_meta, h.box_meta)
   UP(media, h.media)
   UP(medium_brefs, h.medium_brefs)
   UP(materials, h.materials)
@@ -673,6 +685,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.n_nodes = int(h.nodes.size() / 4);
   s.n_spheres = int(h.spheres.size() / 2);
   s.n_quads = int(h.quads.size() / 3);
+  s.n_boxes = int(h.boxes.size() / 3);
   s.n_media = int(h.media.size());
   s.n_materials = int(h.materials.size() / 2);
   s.n_textures = int(h.textures.size() / 2);
@@ -868,7 +881,7 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
   RT_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
   out->rays = c[1];
   out->samples = ctx->samples_total;  // every sample of the requested range is rendered: W*H*count per launch
-  for (int i = 0; i < 14; i++) out->census[i] = c[4 + i];
+  for (int i = 0; i < CN_COUNT; i++) out->census[i] = c[4 + i];
   if (ctx->timed) {
     float ms = 0;
     RT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -879,6 +892,7 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
   out->n_nodes = ctx->sc.n_nodes;
   out->n_spheres = ctx->sc.n_spheres;
   out->n_quads = ctx->sc.n_quads;
+  out->n_boxes = ctx->sc.n_boxes;
   out->n_media = ctx->sc.n_media;
   out->bvh_nodes_in_smem = ctx->smem_nodes;
   out->kernel_launches = ctx->launches;
@@ -991,7 +1005,7 @@ int rt_eval_scatter(rt_ctx* ctx, int32_t material, int64_t n, uint64_t seed, con
 }
 
 // Host-only view of the scene converter, for CPU tests of the host logic (no GPU needed):
-// fills counts[0..7] = nodes, spheres, quads, media, leaf refs, bvh depth, chains, materials.
+// fills counts[0..8] = nodes, spheres, quads, media, leaf refs, bvh depth, chains, materials, boxes.
 int rt_debug_build_stats(const rt_scene_desc* scene, int32_t* counts, double* sah_cost) {
   HostScene h;
   if (!build_host_scene(scene, h)) return RT_ERR_INVALID;
@@ -999,6 +1013,7 @@ int rt_debug_build_stats(const rt_scene_desc* scene, int32_t* counts, double* sa
     counts[0] = int(h.nodes.size() / 4), counts[1] = int(h.spheres.size() / 2), counts[2] = int(h.quads.size() / 3);
     counts[3] = int(h.media.size()), counts[4] = int(h.leaf_refs.size()), counts[5] = h.bvh_depth;
     counts[6] = int(h.xchains.size()), counts[7] = int(h.materials.size() / 2);
+    counts[8] = int(h.boxes.size() / 3);
   }
   if (sah_cost) *sah_cost = h.sah_cost;
   return RT_OK;

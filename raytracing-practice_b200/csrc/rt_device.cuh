@@ -143,6 +143,74 @@ __device__ __forceinline__ float hit_quad(float4 nD, float4 A, float4 B, float3 
   return t;
 }
 
+// box(a, b, mat) (quad.hpp:129-159: six quads) as one slab test in the box's frame.  A translate / rotate_y
+// instance of the box is the 2x2 rotation of (o - t, d) — the per-ray transform of translate::hit / rotate_y::hit
+// (hittable.hpp:86-104), paid only by rays that reach this leaf.  The two roots are where the line
+// crosses the box surface: the smaller one is the closest of the (up to two) quads quad::hit would report.
+struct BoxSlabs {
+  float nx, ny, nz, fx, fy, fz;  // per-axis entry / exit parameters
+  float3 d;                      // direction in the box frame (its signs name the faces)
+  float tn, tf;
+};
+// `inv`, `ood` = 1/d and o/d of the WORLD ray: an unrotated box (translation folded into its bounds) reuses them
+__device__ __forceinline__ bool box_slabs(float4 b0, float4 b1, float4 b2, float3 o, float3 d, float3 inv, float3 ood, int self_face, BoxSlabs& r) {
+  float x0, x1, y0, y1, z0, z1;
+  if (b2.w != 0.0f) {
+    const float3 q = o - xyz(b2);
+    const float c = b0.w, s = b1.w;
+    o = f3(c * q.x - s * q.z, q.y, s * q.x + c * q.z);
+    d = f3(c * d.x - s * d.z, d.y, s * d.x + c * d.z);
+    const float ix = fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x);
+    const float iz = fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z);
+    x0 = (b0.x - o.x) * ix, x1 = (b1.x - o.x) * ix;
+    y0 = (b0.y - o.y) * inv.y, y1 = (b1.y - o.y) * inv.y;  // rotate_y leaves d.y alone: the world 1/d.y serves
+    z0 = (b0.z - o.z) * iz, z1 = (b1.z - o.z) * iz;
+  } else {
+    x0 = fmaf(b0.x, inv.x, -ood.x), x1 = fmaf(b1.x, inv.x, -ood.x);
+    y0 = fmaf(b0.y, inv.y, -ood.y), y1 = fmaf(b1.y, inv.y, -ood.y);
+    z0 = fmaf(b0.z, inv.z, -ood.z), z1 = fmaf(b1.z, inv.z, -ood.z);
+  }
+  if (self_face >= 0) {  // a ray that starts ON that face of this box crosses its plane at exactly 0: no fp32 epsilon
+    if (self_face == 0) x0 = 0.0f; else if (self_face == 1) x1 = 0.0f; else if (self_face == 2) y0 = 0.0f;
+    else if (self_face == 3) y1 = 0.0f; else if (self_face == 4) z0 = 0.0f; else z1 = 0.0f;
+  }
+  r.nx = fminf(x0, x1), r.ny = fminf(y0, y1), r.nz = fminf(z0, z1);
+  r.fx = fmaxf(x0, x1), r.fy = fmaxf(y0, y1), r.fz = fmaxf(z0, z1);
+  r.d = d;
+  r.tn = fmaxf(fmaxf(r.nx, r.ny), r.nz);
+  r.tf = fminf(fminf(r.fx, r.fy), r.fz);
+  return r.tn <= r.tf;
+}
+// quad::hit over the six faces with interval::contains on (tmin, tmax): the entry point if it is inside the
+// interval, else the exit point; returns -1 or t, and the face hit (axis * 2 + hi side)
+__device__ __forceinline__ float hit_box(float4 b0, float4 b1, float4 b2, float3 o, float3 d, float3 inv, float3 ood, float tmin, float tmax, int self_face,
+                                         int& face) {
+  BoxSlabs r;
+  if (!box_slabs(b0, b1, b2, o, d, inv, ood, self_face, r)) return -1.0f;
+  if (r.tn >= tmin && r.tn <= tmax) {  // entry: the axis whose near plane is crossed last, on the side the ray comes from
+    const int a = (r.nx >= r.ny && r.nx >= r.nz) ? 0 : (r.ny >= r.nz ? 1 : 2);
+    const float da = a == 0 ? r.d.x : (a == 1 ? r.d.y : r.d.z);
+    face = a * 2 + (da > 0.0f ? 0 : 1);
+    return r.tn;
+  }
+  if (r.tf >= tmin && r.tf <= tmax) {
+    const int a = (r.fx <= r.fy && r.fx <= r.fz) ? 0 : (r.fy <= r.fz ? 1 : 2);
+    const float da = a == 0 ? r.d.x : (a == 1 ? r.d.y : r.d.z);
+    face = a * 2 + (da > 0.0f ? 1 : 0);
+    return r.tf;
+  }
+  return -1.0f;
+}
+// both surface crossings of the LINE (for medium boundaries)
+__device__ __forceinline__ bool box_roots(float4 b0, float4 b1, float4 b2, float3 o, float3 d, float& r0, float& r1) {
+  const float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
+                        fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+  BoxSlabs r;
+  const bool ok = box_slabs(b0, b1, b2, o, d, inv, o * inv, -1, r);
+  r0 = r.tn, r1 = r.tf;
+  return ok;
+}
+
 // ---------------------------------------------------------------------------------------
 // BVH node access: the first `smem_nodes` nodes (breadth-first = top levels) live in shared
 // memory, the rest is read through the read-only path (L1/L2 resident: the arrays are tiny).
@@ -188,6 +256,10 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
     if ((ref >> 30) == REF_SPHERE) {
       float r0, r1;
       if (sphere_roots(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, r0, r1)) t1 = fminf(t1, r0);
+    } else if ((ref >> 30) == REF_BOX) {
+      float r0, r1;
+      const uint32_t b = idx >> 3;
+      if (box_roots(__ldg(sc.boxes + 3 * b), __ldg(sc.boxes + 3 * b + 1), __ldg(sc.boxes + 3 * b + 2), o, d, r0, r1)) t1 = fminf(t1, r0);
     } else {
       float t = hit_quad(__ldg(sc.quads + 3 * idx), __ldg(sc.quads + 3 * idx + 1), __ldg(sc.quads + 3 * idx + 2), o, d, -INF, INF);
       if (t != -1.0f) t1 = fminf(t1, t);
@@ -204,6 +276,13 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
       float r0, r1;
       if (sphere_roots(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, time, r0, r1)) {
         float t = r0 > lo ? r0 : (r1 > lo ? r1 : INF);
+        t2 = fminf(t2, t);
+      }
+    } else if ((ref >> 30) == REF_BOX) {
+      float r0, r1;
+      const uint32_t b = idx >> 3;
+      if (box_roots(__ldg(sc.boxes + 3 * b), __ldg(sc.boxes + 3 * b + 1), __ldg(sc.boxes + 3 * b + 2), o, d, r0, r1)) {
+        float t = r0 >= lo ? r0 : (r1 >= lo ? r1 : INF);  // quads: interval::contains
         t2 = fminf(t2, t);
       }
     } else {
@@ -248,7 +327,7 @@ constexpr int kStackDepth = 32;
 
 // Census slots of the instrumented build (RT_RENDER_COUNTERS): the N_* of SURVEY.md §8(d).
 enum : int { CN_NODE = 0, CN_SPH = 1, CN_SPH_HIT = 2, CN_QUAD = 3, CN_QUAD_FULL = 4, CN_MEDIUM = 5, CN_LAMB = 6, CN_METAL = 7,
-             CN_DIEL = 8, CN_LIGHT = 9, CN_ISO = 10, CN_TEX_CHECKER = 11, CN_TEX_IMAGE = 12, CN_TEX_NOISE = 13, CN_COUNT = 14 };
+             CN_DIEL = 8, CN_LIGHT = 9, CN_ISO = 10, CN_TEX_CHECKER = 11, CN_TEX_IMAGE = 12, CN_TEX_NOISE = 13, CN_BOX = 14, CN_COUNT = 15 };
 
 // ---------------------------------------------------------------------------------------
 // world.hit(r, interval(tmin, tmax), rec) as a per-lane state machine.
@@ -392,7 +471,16 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
           cn[CN_QUAD]++, cn[CN_QUAD_FULL] += (fabsf(den) >= 1e-8f && tq >= ts.tmin && tq <= ts.best.t) || t != -1.0f;
         }
       }
-    } else if (ref != REF_NONE && media) {
+    } else if (type == REF_BOX) {
+      if (ref != REF_NONE) {
+        const uint32_t b = idx >> 3;
+        const int self_face = ((ts.skip >> 30) == REF_BOX && ts.skip != REF_NONE && ((ts.skip & 0x3FFFFFFFu) >> 3) == b) ? int(ts.skip & 7u) : -1;
+        int face = 0;
+        t = hit_box(__ldg(sc.boxes + 3 * b), __ldg(sc.boxes + 3 * b + 1), __ldg(sc.boxes + 3 * b + 2), o, d, ts.inv, ts.ood, ts.tmin, ts.best.t, self_face, face);
+        if (COUNT) cn[CN_BOX]++;
+        ref = make_ref(REF_BOX, (b << 3) | uint32_t(face));
+      }
+    } else if (media) {
       const DMedium m = sc.media[idx];
       PathKey key;
       uint32_t bounce;
@@ -574,6 +662,24 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
     }
     s.front = dot(d, xyz(nD)) < 0.0f;
     s.n = s.front ? xyz(nD) : -xyz(nD);
+  } else if (type == REF_BOX) {
+    const uint32_t b = idx >> 3, face = idx & 7u;
+    const float4 b0 = __ldg(sc.boxes + 3 * b), b1 = __ldg(sc.boxes + 3 * b + 1), b2 = __ldg(sc.boxes + 3 * b + 2);
+    const int4 meta = __ldg(sc.box_meta + b);
+    const uint32_t fm = (uint32_t(meta.z) >> (4u * face)) & 15u;
+    const float sgn = ((face & 1u) != 0u) != ((fm & 8u) != 0u) ? 1.0f : -1.0f;  // the QUAD's normal: outward unless flagged
+    float3 n = f3((face >> 1) == 0u ? sgn : 0.0f, (face >> 1) == 1u ? sgn : 0.0f, (face >> 1) == 2u ? sgn : 0.0f);
+    if (b2.w != 0.0f) n = f3(b0.w * n.x + b1.w * n.z, n.y, -b1.w * n.x + b0.w * n.z);  // back to world (rotate_y)
+    s.material = meta.x;
+    float4 m1 = __ldg(sc.materials + 2 * s.material + 1);
+    if (__float_as_int(m1.z) & MATF_NEEDS_UV) {
+      const int qi = meta.y + int(fm & 7u);
+      float4 A = __ldg(sc.quads + 3 * qi + 1), B = __ldg(sc.quads + 3 * qi + 2);
+      s.u = dot(xyz(A), s.p) + A.w;
+      s.v = dot(xyz(B), s.p) + B.w;
+    }
+    s.front = dot(d, n) < 0.0f;
+    s.n = s.front ? n : -n;
   } else {  // medium: arbitrary normal, front face
     s.material = sc.media[idx].material;
     s.n = f3(1.0f, 0.0f, 0.0f);

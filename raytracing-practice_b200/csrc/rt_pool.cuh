@@ -344,6 +344,11 @@ __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, fl
         ts.d = f3(PF(PF_DX, tslot), PF(PF_DY, tslot), PF(PF_DZ, tslot));
         ts.time = PF(PF_TIME, tslot);
         ts.skip = (uint32_t)PI(PF_SKIP, tslot);
+        {
+          const float4 s0 = lsc[0], s1 = lsc[32];
+          ts.inv = f3(s0.x, s0.y, s0.z);
+          ts.ood = f3(s0.w, s1.x, s1.y);
+        }
         mode = leaf_step<COUNT>(ts, st, sc, media,
                                 [&](PathKey& k, uint32_t& b) {
                                   k = PathKey{P.key, (uint32_t)CI(PC_PIXEL, tslot), (uint32_t)CI(PC_SAMPLE, tslot)};

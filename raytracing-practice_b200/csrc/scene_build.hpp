@@ -37,6 +37,8 @@ struct HostScene {
   std::vector<int2> sph_meta;
   std::vector<float4> quads;
   std::vector<int> quad_mat;
+  std::vector<float4> boxes;
+  std::vector<int4> box_meta;
   std::vector<DMedium> media;
   std::vector<uint32_t> medium_brefs;
   std::vector<float4> materials;
@@ -186,7 +188,7 @@ struct Builder {
     return true;
   }
 
-  bool add_quad(const rt_hittable& h, const Xform& X) {
+  bool add_quad(const rt_hittable& h, const Xform& X, bool as_item = true) {
     if (h.material < 0 || h.material >= d->n_materials) return fail("quad: bad material index");
     // exact data first: object space, reference operation order (quad.hpp:17-23)
     d3 Qo = ld(h.p), uo = ld(h.p + 3), vo = ld(h.p + 6);
@@ -230,7 +232,84 @@ struct Builder {
     }
     double pad = 5e-5 + 4e-7 * amax;  // thin-axis padding as aabb.hpp:135-154, plus fp32 slack
     for (int a = 0; a < 3; a++) lo[a] -= pad, hi[a] += pad;
-    emit(make_ref(REF_QUAD, uint32_t(idx)), box_from(lo, hi), 1.0f);
+    if (as_item) emit(make_ref(REF_QUAD, uint32_t(idx)), box_from(lo, hi), 1.0f);
+    return true;
+  }
+
+  // box(a, b, mat) (quad.hpp:129-159) is a hittable_list of six quads.  When a list IS such a box — six
+  // axis-aligned rectangles of one material that tile the surface of [lo, hi] in the list's own frame — it
+  // becomes ONE slab-test primitive (REF_BOX): 1 BVH item instead of 6, 1 intersection instead of up to 6.
+  // The six quad records are still written (uv, primitive ids, the fp64 exact predicate), just not as BVH items.
+  // Returns false (nothing emitted) when the list is anything else.
+  bool try_box(const rt_hittable& list, const Xform& X, bool& ok) {
+    if (std::getenv("RT_B200_NO_BOXES")) return false;
+    if (list.child1 != 6) return false;
+    const rt_hittable* q[6];
+    for (int k = 0; k < 6; k++) {
+      int ci = d->child_index[list.child0 + k];
+      if (ci < 0 || ci >= d->n_hittables) return false;
+      q[k] = &d->hittables[ci];
+      if (q[k]->kind != RT_H_QUAD || q[k]->material != q[0]->material) return false;
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < 6; k++)
+      for (int c = 0; c < 4; c++)
+        for (int a = 0; a < 3; a++) {
+          double v = q[k]->p[a] + ((c & 1) ? q[k]->p[3 + a] : 0.0) + ((c & 2) ? q[k]->p[6 + a] : 0.0);
+          lo[a] = std::min(lo[a], v), hi[a] = std::max(hi[a], v);
+        }
+    for (int a = 0; a < 3; a++)
+      if (!(hi[a] > lo[a])) return false;
+    int face_quad[6] = {-1, -1, -1, -1, -1, -1}, face_flip[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 6; k++) {
+      const double* Q = q[k]->p;
+      const double* u = q[k]->p + 3;
+      const double* v = q[k]->p + 6;
+      int au = -1, av = -1;
+      for (int a = 0; a < 3; a++) {
+        if (u[a] != 0) { if (au >= 0) return false; au = a; }
+        if (v[a] != 0) { if (av >= 0) return false; av = a; }
+      }
+      if (au < 0 || av < 0 || au == av) return false;
+      const int an = 3 - au - av;  // the face's constant axis
+      int side;
+      if (Q[an] == lo[an]) side = 0; else if (Q[an] == hi[an]) side = 1; else return false;
+      // the rectangle must span the whole face
+      for (int a : {au, av}) {
+        const double e = a == au ? u[a] : v[a];
+        const double x0 = std::min(Q[a], Q[a] + e), x1 = std::max(Q[a], Q[a] + e);
+        if (x0 != lo[a] || x1 != hi[a]) return false;
+      }
+      const int f = an * 2 + side;
+      if (face_quad[f] >= 0) return false;
+      face_quad[f] = k;
+      d3 n = cross(ld(u), ld(v));
+      const double nn = an == 0 ? n.x : (an == 1 ? n.y : n.z);
+      face_flip[f] = (nn > 0) == (side == 1) ? 0 : 1;  // 1: the quad's normal points INTO the box
+    }
+    const int first_quad = int(out->quads.size() / 3);
+    for (int k = 0; k < 6 && ok; k++) ok = add_quad(*q[k], X, false);
+    if (!ok) return true;
+    int map = 0;
+    for (int f = 0; f < 6; f++) map |= (face_quad[f] | (face_flip[f] << 3)) << (4 * f);
+    const int idx = int(out->boxes.size() / 3);
+    const bool xf = X.rotated;
+    // an unrotated box takes the translation into its bounds and needs no ray transform at all
+    const d3 t = xf ? X.t : d3{0, 0, 0};
+    const d3 sh = xf ? d3{0, 0, 0} : X.t;
+    out->boxes.push_back(float4{float(lo[0] + sh.x), float(lo[1] + sh.y), float(lo[2] + sh.z), float(xf ? X.c : 1.0)});
+    out->boxes.push_back(float4{float(hi[0] + sh.x), float(hi[1] + sh.y), float(hi[2] + sh.z), float(xf ? X.s : 0.0)});
+    out->boxes.push_back(float4{float(t.x), float(t.y), float(t.z), xf ? 1.0f : 0.0f});
+    out->box_meta.push_back(int4{q[0]->material, first_quad, map, 0});
+    double wlo[3] = {1e300, 1e300, 1e300}, whi[3] = {-1e300, -1e300, -1e300}, amax = 0;
+    for (int c = 0; c < 8; c++) {
+      d3 p = X.point(d3{(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]});
+      const double pc[3] = {p.x, p.y, p.z};
+      for (int a = 0; a < 3; a++) wlo[a] = std::min(wlo[a], pc[a]), whi[a] = std::max(whi[a], pc[a]), amax = std::max(amax, std::fabs(pc[a]));
+    }
+    const double pad = 5e-5 + 4e-7 * amax;
+    for (int a = 0; a < 3; a++) wlo[a] -= pad, whi[a] += pad;
+    emit(make_ref(REF_BOX, (uint32_t(idx) << 3) | 7u), box_from(wlo, whi), 1.5f);
     return true;
   }
 
@@ -244,6 +323,7 @@ struct Builder {
       case RT_H_QUAD: ok = add_quad(h, X); break;
       case RT_H_LIST:
         if (h.child0 < 0 || h.child1 < 0 || h.child0 + h.child1 > d->n_child_index) { ok = fail("list: bad child range"); break; }
+        if (try_box(h, X, ok)) break;
         for (int k = 0; k < h.child1 && ok; k++) ok = visit(d->child_index[h.child0 + k], X);
         break;
       case RT_H_BVH:

@@ -88,12 +88,13 @@ def test_jpeg_decoder_subsampled_and_restart_files(rtb, built, tmp_path):
 def test_scene_converter_counts_and_errors(rtb, built):
     lib = C.CDLL(rtb.CUDA_LIB_PATH)
     lib.rt_debug_build_stats.argtypes = [C.POINTER(rtb.rt_scene_desc), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
-    want = {"bouncing_spheres": (484, 0, 0), "cornell_box": (0, 18, 0), "cornell_smoke": (0, 18, 2), "book2_final": (1008, 2401, 2)}
-    for name, (ns, nq, nm) in want.items():
+    # spheres, quad records, media, box() lists recognised as one slab-test primitive (quad.hpp:129-159)
+    want = {"bouncing_spheres": (484, 0, 0, 0), "cornell_box": (0, 18, 0, 2), "cornell_smoke": (0, 18, 2, 2), "book2_final": (1008, 2401, 2, 400)}
+    for name, (ns, nq, nm, nb) in want.items():
         sc = rtb.Scene(name, rand_seed=1)
-        cnt = (C.c_int32 * 8)()
+        cnt = (C.c_int32 * 16)()
         assert lib.rt_debug_build_stats(sc.desc, cnt, None) == 0
-        assert (cnt[1], cnt[2], cnt[3]) == (ns, nq, nm), name
+        assert (cnt[1], cnt[2], cnt[3], cnt[8]) == (ns, nq, nm, nb), name
         assert 1 <= cnt[0] <= max(1, ns + nq) and cnt[5] <= 32  # nodes, depth within the traversal stack
     import scene_util as su
 
