@@ -51,6 +51,9 @@ struct RenderParams {
 #define RT_THREADS 1024
 #endif
 constexpr int kRenderThreads = RT_THREADS;
+#ifndef RT_OUTLINED_TRAVERSAL
+#define RT_OUTLINED_TRAVERSAL 0
+#endif
 #ifndef RT_DEFAULT_POOL
 #define RT_DEFAULT_POOL 0
 #endif
@@ -70,6 +73,10 @@ __device__ __forceinline__ long long to_fixed(float v) {
 template <bool COUNT>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
+#if RT_OUTLINED_TRAVERSAL
+  __shared__ DeviceScene s_sc;  // closest_hit_outlined cannot address the kernel's constant bank
+  for (int i = threadIdx.x; i < int(sizeof(DeviceScene) / 4); i += blockDim.x) reinterpret_cast<int*>(&s_sc)[i] = reinterpret_cast<const int*>(&P.sc)[i];
+#endif
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
   __syncthreads();
   const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
@@ -155,7 +162,13 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
     const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;  // Philox counter word: 1, 2, ...
     if (alive) n_rays++;
+#if RT_OUTLINED_TRAVERSAL  // measured: -3 % (gpurun_out/ab_outlined.log); kept for the record
+    Hit h{INF, REF_NONE};
+    if (alive && media) h = sample_global_media<COUNT>(sc, o, d, time, 0.001f, INF, key, bounce, cn);
+    h = closest_hit_outlined<COUNT>(&s_sc, s_nodes, P.smem_nodes, o, d, time, skip, h, P.key, key.pixel, key.sample, bounce, alive, cn);
+#else
     Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive);
+#endif
     if (alive) {
       if (h.ref == REF_NONE) {
         L = L + beta * P.cam.bg;

@@ -46,7 +46,7 @@ __device__ __forceinline__ float3 normalize3(float3 a) { return rsqrtf(dot(a, a)
 #ifndef RT_OUTLINE_PHILOX
 #define RT_OUTLINE_PHILOX RT_OUTLINE
 #endif
-__device__ RT_OUTLINE_PHILOX uint4 philox4x32_10(uint4 ctr, uint2 key) {
+__device__ __forceinline__ uint4 philox4x32_10_inl(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -58,6 +58,7 @@ __device__ RT_OUTLINE_PHILOX uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+__device__ RT_OUTLINE_PHILOX uint4 philox4x32_10(uint4 ctr, uint2 key) { return philox4x32_10_inl(ctr, key); }
 // 24-bit uniform in [0,1): same granularity as the reference's int/float random_double
 // (rtweekend.hpp:26) but never exactly 1.0.
 __device__ __forceinline__ float u01(uint32_t x) { return float(x >> 8) * 5.9604644775390625e-8f; }
@@ -69,6 +70,10 @@ struct PathKey {
 };
 __device__ __forceinline__ uint4 rng_block(const PathKey& k, uint32_t bounce, uint32_t stream) {
   return philox4x32_10(make_uint4(k.pixel, k.sample, bounce, stream), k.key);
+}
+// the same block with the generator inlined: for code that must stay CALL-FREE (see closest_hit_outlined)
+__device__ __forceinline__ uint4 rng_block_inl(const PathKey& k, uint32_t bounce, uint32_t stream) {
+  return philox4x32_10_inl(make_uint4(k.pixel, k.sample, bounce, stream), k.key);
 }
 
 // uniform direction on the unit sphere from two uniforms: distribution-identical to the
@@ -295,8 +300,9 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
 
 // Per-ray uniforms for media: medium k owns component (k & 3) of Philox block stream 1 + (k >> 2)
 // of the ray's (pixel, sample, bounce) counter.
+template <bool CALLFREE = false>
 __device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bounce, int medium) {
-  uint4 r = rng_block(key, bounce, 1u + (uint32_t(medium) >> 2));
+  uint4 r = CALLFREE ? rng_block_inl(key, bounce, 1u + (uint32_t(medium) >> 2)) : rng_block(key, bounce, 1u + (uint32_t(medium) >> 2));
   uint32_t c = uint32_t(medium) & 3u;
   return u01(c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w)));
 }
@@ -304,8 +310,9 @@ __device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bou
 // The free-flight uniform is drawn LAZILY, only once the ray is known to cross the medium inside
 // [tmin, tmax]: most BVH-leaf visits of a medium's bounding box miss the boundary itself, and the
 // Philox block was 2/3 of this function's instructions (profiles/r06_pool_first.md).
-__device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& m, int mi, float3 o, float3 d, float time, float tmin, float tmax,
-                                          const PathKey& key, uint32_t bounce) {
+template <bool CALLFREE>
+__device__ __forceinline__ float medium_sample_impl(const DeviceScene& sc, const DMedium& m, int mi, float3 o, float3 d, float time, float tmin, float tmax,
+                                                    const PathKey& key, uint32_t bounce) {
   float t1, t2;
   if (!medium_span(sc, m, o, d, time, t1, t2)) return -1.0f;
   t1 = fmaxf(t1, tmin);
@@ -314,10 +321,14 @@ __device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& 
   t1 = fmaxf(t1, 0.0f);
   float len = sqrtf(dot(d, d));
   float inside = (t2 - t1) * len;
-  const float u = medium_uniform(key, bounce, mi);
+  const float u = medium_uniform<CALLFREE>(key, bounce, mi);
   float hit_distance = m.neg_inv_density * __logf(u);  // u == 0 -> +inf -> miss, as log(0) in the reference
   if (!(hit_distance <= inside)) return -1.0f;
   return t1 + hit_distance / len;
+}
+__device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& m, int mi, float3 o, float3 d, float time, float tmin, float tmax,
+                                          const PathKey& key, uint32_t bounce) {
+  return medium_sample_impl<false>(sc, m, mi, o, d, time, tmin, tmax, key, bounce);
 }
 
 constexpr int kStackDepth = 32;
@@ -450,7 +461,7 @@ __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const Nod
 
 // leaf: ~cur = (first << 3) | (count - 1)
 // `key_of(key, bounce)` yields the ray's Philox counter; it is only called when a medium is actually sampled
-template <bool COUNT, typename KeyFn>
+template <bool COUNT, bool CALLFREE = false, typename KeyFn>
 __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn) {
   const int code = ~ts.cur;
   const int first = code >> 3, count = (code & 7) + 1;
@@ -485,7 +496,8 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
       PathKey key;
       uint32_t bounce;
       key_of(key, bounce);
-      t = medium_sample(sc, m, int(idx), o, d, ts.time, ts.tmin, ts.best.t, key, bounce);
+      t = CALLFREE ? medium_sample_impl<true>(sc, m, int(idx), o, d, ts.time, ts.tmin, ts.best.t, key, bounce)
+                   : medium_sample(sc, m, int(idx), o, d, ts.time, ts.tmin, ts.best.t, key, bounce);
       if (COUNT) cn[CN_MEDIUM]++;
     }
     if (t != -1.0f) ts.best = Hit{t, ref};
@@ -499,7 +511,7 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
 // the warp converged (exited lanes excepted).  With plain per-lane `continue`s the compiler never
 // re-merged the lanes: ncu showed 4.75 of 32 active per instruction (profiles/r01_*.md).
 // `ts` holds a ray (trav_set_ray) and its closest hit so far (ts.best); lanes with active == false only vote
-template <bool COUNT>
+template <bool COUNT, bool CALLFREE = false>
 __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const NodeSource& ns, TravState& ts, bool media, const PathKey& key,
                                                     uint32_t bounce, unsigned int* cn, bool active) {
   const unsigned FULL = 0xFFFFFFFFu;
@@ -512,10 +524,27 @@ __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const
     if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
       if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
     } else {
-      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT, CALLFREE>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
     }
   }
   return ts.best;
+}
+
+// The production traversal as an OUTLINED, CALL-FREE function.  Inlined into a kernel that also calls other
+// outlined helpers (Philox, perlin, media), ptxas homes every value that lives across those calls in local memory
+// — the node index, 1/d, o/d — and each node step paid 6 LDL + 2 STL for it (profiles/r09_*.md).  With its own
+// register allocation and no call inside, the node loop touches local memory only for the traversal stack.
+// `sc`, `ns` must be addressable from a function: the kernel passes its shared-memory copy of the parameters.
+template <bool COUNT>
+__device__ __noinline__ Hit closest_hit_outlined(const DeviceScene* __restrict__ sc, const float4* s_nodes, int smem_nodes, float3 o, float3 d, float time,
+                                                 uint32_t skip, Hit best, uint2 seed, uint32_t pixel, uint32_t sample, uint32_t bounce, bool active,
+                                                 unsigned int* cn) {
+  TravState ts;
+  trav_set_ray(ts, o, d, time, 0.001f, skip);
+  ts.best = best;
+  const NodeSource ns{s_nodes, sc->nodes, smem_nodes};
+  const PathKey key{seed, pixel, sample};
+  return closest_hit_prepared<COUNT, true>(*sc, ns, ts, sc->n_media != 0, key, bounce, cn, active);
 }
 
 template <bool COUNT>
