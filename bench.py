@@ -30,9 +30,11 @@ METRIC = "samples_px_per_s"
 UNIT = "samples*px/s"
 # flop-equivalents per unit of algorithmic work (one slab test = 12 flop + 12 cmp/sel)
 F_BOX, F_SPH_MISS, F_SPH_HIT, F_QUAD_EARLY, F_QUAD_FULL, F_MEDIUM = 24, 29, 60, 12, 54, 120
+F_BOXPRIM = 36  # a box() primitive: one slab test (24) + the entry/exit interval test and face pick (12)
 F_SHADE = dict(lambertian=15, metal=35, dielectric=60, light=0, isotropic=15, checker=10, image=6, noise=1550, bounce=6)
 # bytes per unit (fp32 device layouts): BVH2 node with both child boxes 64 B, sphere 32 B, quad 48 B
 B_NODE, B_SPH, B_QUAD, B_TEXEL, B_PERLIN = 64, 32, 48, 4, 56 * 16 + 7 * 24
+B_BOXPRIM = 48
 
 
 def parse():
@@ -279,17 +281,29 @@ def main():
     scene_bytes += 4 * sc.desc.contents.n_child_index
     for k in range(sc.desc.contents.n_images):
         scene_bytes += 3 * sc.desc.contents.images[k].width * sc.desc.contents.images[k].height
+    ctx.upload_scene(sc.desc)  # untimed warm-up of the host-buffer calls (first-use module loads of the download kernels)
+    ctx.render(cam, seed=99, sample_begin=begin, sample_count=min(count, 4), clear=True)
+    if rank == 0:
+        ctx.download_rgb8(spp)
     barrier()
     t0 = time.time()
+    e2e_parts = [0.0, 0.0, 0.0, 0.0]  # upload, render, reduce, download (seconds, this rank)
     for i in range(e2e_steps):
+        ta = time.time()
         ctx.upload_scene(sc.desc)  # host scene description -> device (H2D)
+        tb = time.time()
         ctx.render(cam, seed=i, sample_begin=begin, sample_count=count, clear=True)
         ctx.synchronize()
+        tc = time.time()
         if world > 1:
             dist.reduce_accum_to_rank0(ctx.accum_tensor())
             torch.cuda.synchronize()
+        td = time.time()
         if rank == 0:
             rgb = ctx.download_rgb8(spp)  # finished image -> host (D2H)
+        te = time.time()
+        for k, dt in enumerate((tb - ta, tc - tb, td - tc, te - td)):
+            e2e_parts[k] += dt / e2e_steps
     barrier()
     e2e_sec = (time.time() - t0) / e2e_steps
 
@@ -301,13 +315,14 @@ def main():
         st = ctx.stats()
         cs = list(st.census)
         r = max(st.rays, 1)
-        keys = ["node", "sph", "sph_hit", "quad", "quad_full", "medium", "lambertian", "metal", "dielectric", "light", "isotropic", "checker", "image", "noise"]
+        keys = ["node", "sph", "sph_hit", "quad", "quad_full", "medium", "lambertian", "metal", "dielectric", "light", "isotropic", "checker", "image", "noise", "box"]
         per_ray = {k: cs[i] / r for i, k in enumerate(keys)}
         flops = (2 * F_BOX * per_ray["node"] + F_SPH_MISS * (per_ray["sph"] - per_ray["sph_hit"]) + F_SPH_HIT * per_ray["sph_hit"]
                  + F_QUAD_EARLY * (per_ray["quad"] - per_ray["quad_full"]) + F_QUAD_FULL * per_ray["quad_full"] + F_MEDIUM * per_ray["medium"]
                  + sum(F_SHADE[k] * per_ray[k] for k in ("lambertian", "metal", "dielectric", "light", "isotropic", "checker", "image", "noise"))
-                 + F_SHADE["bounce"])
-        nbytes = (B_NODE * per_ray["node"] + B_SPH * per_ray["sph"] + B_QUAD * per_ray["quad"] + B_TEXEL * per_ray["image"] + B_PERLIN * per_ray["noise"])
+                 + F_BOXPRIM * per_ray["box"] + F_SHADE["bounce"])
+        nbytes = (B_NODE * per_ray["node"] + B_SPH * per_ray["sph"] + B_QUAD * per_ray["quad"] + B_BOXPRIM * per_ray["box"] + B_TEXEL * per_ray["image"]
+                  + B_PERLIN * per_ray["noise"])
         census = dict(per_ray=per_ray, flops_per_ray=flops, bytes_per_ray=nbytes, rays_per_sample=st.rays / max(st.samples, 1))
 
     # ---- max over ranks -------------------------------------------------------------------------
@@ -351,7 +366,8 @@ def main():
                        "l2": "256 MB device write between timed steps (flush)", "seed": "Philox key = step index"},
             "mrays_per_s": mrays, "rays_per_sample": rays_per_step / total_samples, "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": total_samples / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(W * H * 3),
-                    "steps": e2e_steps, "path": "rt_upload_scene + rt_render + reduce + rt_download(RGB8) with host buffers, wall clock"},
+                    "steps": e2e_steps, "path": "rt_upload_scene + rt_render + reduce + rt_download(RGB8) with host buffers, wall clock",
+                    "rank0_ms": dict(zip(("upload", "render", "reduce", "download"), (round(1e3 * x, 2) for x in e2e_parts)))},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if not args.no_cpu_baseline and world == 1:
         try:

@@ -48,7 +48,7 @@ struct RenderParams {
 };
 
 #ifndef RT_THREADS
-#define RT_THREADS 1024
+#define RT_THREADS 896  // 28 warps x 72 registers: +6 % over 1024 x 64 on the Book-2 scene since the box primitive (gpurun_out/ab_threads.log)
 #endif
 constexpr int kRenderThreads = RT_THREADS;
 #ifndef RT_OUTLINED_TRAVERSAL
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
 
-  // Per-lane path state, kept small on purpose: the kernel runs 1024 threads per SM (64 registers),
-  // which measured 9-23 % faster than 512 threads with twice the registers (tools/ab_variants.py).
+  // Per-lane path state, kept small on purpose: the kernel runs 896 threads per SM (72 registers); 1024 x 64 was
+  // best before the box primitive grew the leaf code, 512 x 128 is 9-23 % slower (tools/ab_variants.py).
   unsigned int item = blockIdx.x * blockDim.x + threadIdx.x;  // n_items < 2^32 is checked by the host
   int pixel = -1, s = 0, s_end = 0;
   bool alive = false;

@@ -349,7 +349,7 @@ __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, fl
           ts.inv = f3(s0.x, s0.y, s0.z);
           ts.ood = f3(s0.w, s1.x, s1.y);
         }
-        mode = leaf_step<COUNT>(ts, st, sc, media,
+        mode = leaf_step<COUNT, true>(ts, st, sc, media,
                                 [&](PathKey& k, uint32_t& b) {
                                   k = PathKey{P.key, (uint32_t)CI(PC_PIXEL, tslot), (uint32_t)CI(PC_SAMPLE, tslot)};
                                   b = uint32_t(P.cam.max_depth - CI(PC_DEPTH, tslot)) + 1u;

@@ -198,3 +198,55 @@ def test_cpp_drop_in_camera_render(rtb, gpu_ctx, tmp_path):
         gpu_ctx.upload_scene(sc.desc)
         gpu_ctx.render(cam, seed=0)
         assert np.array_equal(img, gpu_ctx.download_rgb8(40).astype(np.int64))
+
+
+@pytest.mark.parametrize("name,width,spp", [("book2_final", 160, 48), ("cornell_smoke", 96, 40), ("bouncing_spheres", 200, 24), ("earth", 120, 16)])
+def test_pool_kernel_is_bit_identical_to_the_megakernel(rtb, gpu_ctx, name, width, spp):
+    """Both render kernels (one path per lane / per-warp path pool, csrc/rt_pool.cuh) use the same Philox
+    keys and the same fixed-point sums: same accumulator bits, same ray count, also on a sample shard."""
+    sc = rtb.Scene(name, rand_seed=1)
+    cam = sc.camera_copy(image_width=width, samples_per_pixel=spp)
+    gpu_ctx.upload_scene(sc.desc)
+    out = {}
+    for tag, flags in (("mega", rtb.RT_RENDER_MEGAKERNEL), ("pool", rtb.RT_RENDER_POOL)):
+        gpu_ctx.render(cam, seed=11, flags=flags)
+        out[tag] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
+        gpu_ctx.render(cam, seed=11, flags=flags, sample_begin=5, sample_count=7)
+        out[tag + "_shard"] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
+    assert out["mega"][1] == out["pool"][1] and np.array_equal(out["mega"][0], out["pool"][0])
+    assert out["mega_shard"][1] == out["pool_shard"][1] and np.array_equal(out["mega_shard"][0], out["pool_shard"][0])
+    cam.max_depth = 0
+    gpu_ctx.render(cam, seed=11, flags=rtb.RT_RENDER_POOL)
+    assert not gpu_ctx.download_accum().any() and gpu_ctx.stats().rays == 0
+
+
+def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
+    """box() lists (quad.hpp:129-159) are flattened to ONE slab-test primitive.  With RT_B200_NO_BOXES the
+    same lists stay six quads: the exact primary pass must agree on every pixel (ids, t, normal — the exact
+    predicate always evaluates the six reference quads), the fp32 production traversal on all but grazing
+    pixels, and the rendered means within Monte-Carlo noise."""
+    res = {}
+    for tag in ("boxes", "quads"):
+        if tag == "quads":
+            monkeypatch.setenv("RT_B200_NO_BOXES", "1")
+        for name in ("cornell_rotated", "book2_final"):
+            sc = rtb.Scene(name, rand_seed=1)
+            cam = sc.camera_copy(image_width=128, samples_per_pixel=256)
+            gpu_ctx.upload_scene(sc.desc)
+            st0 = gpu_ctx.stats()
+            exact = gpu_ctx.primary_visibility(cam)
+            fp32 = gpu_ctx.primary_visibility(cam, flags=rtb.RT_TRACE_FP32 | rtb.RT_TRACE_SKIP_MEDIA)
+            gpu_ctx.render(cam, seed=5)
+            res[tag, name] = (exact, fp32, gpu_ctx.download_radiance(256).astype(np.float64), st0.n_boxes, gpu_ctx.stats().rays)
+    monkeypatch.delenv("RT_B200_NO_BOXES")
+    for name, n_boxes in (("cornell_rotated", 2), ("book2_final", 400)):
+        b, q = res["boxes", name], res["quads", name]
+        assert b[3] == n_boxes and q[3] == 0
+        assert np.array_equal(b[0][0], q[0][0]) and np.array_equal(b[0][1], q[0][1]) and np.array_equal(b[0][2], q[0][2])
+        hit = b[0][0] >= 0
+        assert (b[1][0] != b[0][0]).mean() <= 1e-3  # fp32 vs exact ids
+        same = hit & (b[1][0] == b[0][0])
+        assert np.allclose(b[1][1][same], b[0][1][same], rtol=2e-4) and np.allclose(b[1][2][same], b[0][2][same], atol=2e-4)
+        # two 256-spp estimates of the same image with DIFFERENT fp32 roundings at the hit points
+        assert abs(b[2].mean() - q[2].mean()) < 0.02 * q[2].mean() + 1e-3
+        assert abs(b[4] - q[4]) / q[4] < 0.01
