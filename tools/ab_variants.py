@@ -10,7 +10,7 @@ if sys.argv[1] == "build":
     procs = []
     for spec in sys.argv[2:]:
         tag, _, flags = spec.partition(":")
-        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-use_fast_math", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
                "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "raytracing-practice_b200", "csrc", "rt_b200.cu"), "-o", os.path.join(VDIR, f"{tag}.so")] + flags.split()
         procs.append((tag, subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True)))
     for tag, p in procs:
