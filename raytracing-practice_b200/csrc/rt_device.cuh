@@ -309,7 +309,7 @@ __device__ __forceinline__ float medium_uniform(const PathKey& key, uint32_t bou
 
 // The free-flight uniform is drawn LAZILY, only once the ray is known to cross the medium inside
 // [tmin, tmax]: most BVH-leaf visits of a medium's bounding box miss the boundary itself, and the
-// Philox block was 2/3 of this function's instructions (profiles/r06_pool_first.md).
+// Philox block was 2/3 of this function's instructions (profiles/r06_pool_kernel.md).
 template <bool CALLFREE>
 __device__ __forceinline__ float medium_sample_impl(const DeviceScene& sc, const DMedium& m, int mi, float3 o, float3 d, float time, float tmin, float tmax,
                                                     const PathKey& key, uint32_t bounce) {
@@ -532,7 +532,7 @@ __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const
 
 // The production traversal as an OUTLINED, CALL-FREE function.  Inlined into a kernel that also calls other
 // outlined helpers (Philox, perlin, media), ptxas homes every value that lives across those calls in local memory
-// — the node index, 1/d, o/d — and each node step paid 6 LDL + 2 STL for it (profiles/r09_*.md).  With its own
+// — the node index, 1/d, o/d — and each node step paid 6 LDL + 2 STL for it (profiles/r06_pool_kernel.md).  With its own
 // register allocation and no call inside, the node loop touches local memory only for the traversal stack.
 // `sc`, `ns` must be addressable from a function: the kernel passes its shared-memory copy of the parameters.
 template <bool COUNT>

@@ -259,7 +259,7 @@ __device__ __noinline__ bool shade_phase(const RenderParams* __restrict__ Pp, fl
 
 // TRACE phase of one warp.  Outlined and CALL-FREE on purpose: with any call in the same function ptxas homes
 // every value that lives across it (node index, stack pointer, 1/d ...) in local memory and each node step
-// pays for it (profiles/r06_pool_first.md); here the whole phase gets its own register allocation.
+// pays for it (profiles/r06_pool_kernel.md); here the whole phase gets its own register allocation.
 template <bool COUNT>
 __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, float* __restrict__ pool, float* __restrict__ cold, const float4* s_nodes,
                                          TravStack& st, unsigned int* cn) {
