@@ -258,8 +258,12 @@ struct Builder {
           double v = q[k]->p[a] + ((c & 1) ? q[k]->p[3 + a] : 0.0) + ((c & 2) ? q[k]->p[6 + a] : 0.0);
           lo[a] = std::min(lo[a], v), hi[a] = std::max(hi[a], v);
         }
-    for (int a = 0; a < 3; a++)
+    double tol = 0;  // box() builds its corners as min + (max - min): equal to max only up to double rounding
+    for (int a = 0; a < 3; a++) {
       if (!(hi[a] > lo[a])) return false;
+      tol = std::max(tol, 1e-12 * std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+    }
+    auto near = [tol](double x, double y) { return std::fabs(x - y) <= tol; };
     int face_quad[6] = {-1, -1, -1, -1, -1, -1}, face_flip[6] = {0, 0, 0, 0, 0, 0};
     for (int k = 0; k < 6; k++) {
       const double* Q = q[k]->p;
@@ -273,12 +277,12 @@ struct Builder {
       if (au < 0 || av < 0 || au == av) return false;
       const int an = 3 - au - av;  // the face's constant axis
       int side;
-      if (Q[an] == lo[an]) side = 0; else if (Q[an] == hi[an]) side = 1; else return false;
+      if (near(Q[an], lo[an])) side = 0; else if (near(Q[an], hi[an])) side = 1; else return false;
       // the rectangle must span the whole face
       for (int a : {au, av}) {
         const double e = a == au ? u[a] : v[a];
         const double x0 = std::min(Q[a], Q[a] + e), x1 = std::max(Q[a], Q[a] + e);
-        if (x0 != lo[a] || x1 != hi[a]) return false;
+        if (!near(x0, lo[a]) || !near(x1, hi[a])) return false;
       }
       const int f = an * 2 + side;
       if (face_quad[f] >= 0) return false;

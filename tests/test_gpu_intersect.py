@@ -128,3 +128,36 @@ def test_medium_boundary_spans(rtb, orc, gpu_ctx):
             assert np.quantile(np.abs(t1[both] - o1[both]) / scale, 0.999) <= 1e-5 * 10
             assert np.quantile(np.abs(t2[both] - o2[both]) / scale, 0.999) <= 1e-5 * 10
             assert np.median(np.abs(t2[both] - o2[both]) / scale) <= 1e-6
+
+
+def test_large_scene_bvh_beyond_shared_memory(rtb, orc, gpu_ctx):
+    """20,000 spheres + 300 instanced boxes: ~13 k BVH nodes = 0.85 MB, four times what fits in a CTA's shared
+    memory, so the lower levels are fetched through L1/L2 (load_node's global branch) and the stacks run deep.
+    Exact closest hit against the oracle's linear scan, the fp32 production traversal against the exact one,
+    and both render kernels against each other."""
+    rng = np.random.default_rng(21)
+    s = su.SceneDesc()
+    mat = s.lambertian(s.solid(0.6, 0.5, 0.4))
+    kids = [s.sphere(tuple(rng.uniform(-40, 40, 3)), float(rng.uniform(0.1, 1.2)), mat) for _ in range(20_000)]
+    for _ in range(300):
+        b = s.box(tuple(rng.uniform(-1.5, 0, 3)), tuple(rng.uniform(0.3, 1.5, 3)), mat)
+        kids.append(s.translate(s.rotate_y(b, float(rng.uniform(-90, 90))), tuple(rng.uniform(-40, 40, 3))))
+    desc = s.finish(s.list(kids))
+    gpu_ctx.upload_scene(desc)
+    st = gpu_ctx.stats()
+    assert st.n_boxes == 300 and st.n_nodes * 64 > 300_000 and st.bvh_nodes_in_smem < st.n_nodes
+    n = 20_000
+    o = rng.uniform(-45, 45, (n, 3))
+    d = (rng.uniform(-40, 40, (n, 3)) - o) * rng.uniform(0.05, 2.0, (n, 1))
+    ids, t, nrm, ff = gpu_ctx.trace_rays(o, d, None, 0.001, np.inf, rtb.RT_TRACE_EXACT)
+    oi, ot, on, of, _ = orc.hit_rays(desc, o, d, None, 0.001, np.inf)
+    assert np.array_equal(ids, oi) and (oi >= 0).mean() > 0.5
+    hit = oi >= 0
+    assert np.array_equal(t[hit], ot[hit]) and np.array_equal(nrm[hit], on[hit])
+    ids32, t32, _, _ = gpu_ctx.trace_rays(o, d, None, 0.001, np.inf, rtb.RT_TRACE_FP32)
+    assert (ids32 == oi).mean() >= 0.999
+    cam = su.camera(width=160, spp=8, depth=6, lookfrom=(0, 0, 70), vfov=60.0)
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_MEGAKERNEL)
+    a, r = gpu_ctx.download_accum(), gpu_ctx.stats().rays
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_POOL)
+    assert np.array_equal(a, gpu_ctx.download_accum()) and r == gpu_ctx.stats().rays and a.any()
