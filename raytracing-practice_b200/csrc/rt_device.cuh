@@ -38,6 +38,9 @@ __device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x,
 __device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 __device__ __forceinline__ float3 normalize3(float3 a) { return rsqrtf(dot(a, a)) * a; }
+// 1/x as ONE MUFU.RCP (1 ulp): the IEEE __frcp_rn is a Newton step plus a denormal slow-path call, ~10 instructions
+// at every use, and the production fp32 path has no use for the last bit (the exact predicate is fp64)
+__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 
 // ---------------------------------------------------------------------------------------
 // Philox-4x32-10 (Salmon et al. 2011), counter-based: the sample set of a (pixel, sample,
@@ -101,7 +104,7 @@ __device__ __forceinline__ float hit_sphere(float4 g0, float4 g1, float3 o, floa
   float3 oc = o - c;
   float a = dot(d, d);
   float b = dot(oc, d);
-  float inv_a = __frcp_rn(a);
+  float inv_a = rcp_fast(a);
   if (self) {
     float t = -2.0f * b * inv_a;
     return (t > tmin && t < tmax) ? t : -1.0f;
@@ -124,7 +127,7 @@ __device__ __forceinline__ bool sphere_roots(float4 g0, float4 g1, float3 o, flo
   float3 oc = o - c;
   float a = dot(d, d);
   float b = dot(oc, d);
-  float inv_a = __frcp_rn(a);
+  float inv_a = rcp_fast(a);
   float3 l = fma3(-b * inv_a, d, oc);
   float disc = fmaf(g0.w, g0.w, -dot(l, l));
   if (disc < 0.0f) return false;
@@ -165,8 +168,8 @@ __device__ __forceinline__ bool box_slabs(float4 b0, float4 b1, float4 b2, float
     const float c = b0.w, s = b1.w;
     o = f3(c * q.x - s * q.z, q.y, s * q.x + c * q.z);
     d = f3(c * d.x - s * d.z, d.y, s * d.x + c * d.z);
-    const float ix = fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x);
-    const float iz = fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z);
+    const float ix = fabsf(d.x) > 1e-30f ? rcp_fast(d.x) : copysignf(1e30f, d.x);
+    const float iz = fabsf(d.z) > 1e-30f ? rcp_fast(d.z) : copysignf(1e30f, d.z);
     x0 = (b0.x - o.x) * ix, x1 = (b1.x - o.x) * ix;
     y0 = (b0.y - o.y) * inv.y, y1 = (b1.y - o.y) * inv.y;  // rotate_y leaves d.y alone: the world 1/d.y serves
     z0 = (b0.z - o.z) * iz, z1 = (b1.z - o.z) * iz;
@@ -208,8 +211,8 @@ __device__ __forceinline__ float hit_box(float4 b0, float4 b1, float4 b2, float3
 }
 // both surface crossings of the LINE (for medium boundaries)
 __device__ __forceinline__ bool box_roots(float4 b0, float4 b1, float4 b2, float3 o, float3 d, float& r0, float& r1) {
-  const float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
-                        fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+  const float3 inv = f3(fabsf(d.x) > 1e-30f ? rcp_fast(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? rcp_fast(d.y) : copysignf(1e30f, d.y),
+                        fabsf(d.z) > 1e-30f ? rcp_fast(d.z) : copysignf(1e30f, d.z));
   BoxSlabs r;
   const bool ok = box_slabs(b0, b1, b2, o, d, inv, o * inv, -1, r);
   r0 = r.tn, r1 = r.tf;
@@ -378,8 +381,8 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
 // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
 __device__ __forceinline__ void trav_set_ray(TravState& ts, float3 o, float3 d, float time, float tmin, uint32_t skip) {
   ts.o = o, ts.d = d, ts.time = time, ts.tmin = tmin, ts.skip = skip;
-  ts.inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
-              fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+  ts.inv = f3(fabsf(d.x) > 1e-30f ? rcp_fast(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? rcp_fast(d.y) : copysignf(1e30f, d.y),
+              fabsf(d.z) > 1e-30f ? rcp_fast(d.z) : copysignf(1e30f, d.z));
   ts.ood = o * ts.inv;
 }
 
@@ -665,7 +668,7 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
     float4 g0 = __ldg(sc.spheres + 2 * idx), g1 = __ldg(sc.spheres + 2 * idx + 1);
     int2 meta = __ldg(sc.sph_meta + idx);
     float3 c = fma3(time, xyz(g1), xyz(g0));
-    float3 outward = __frcp_rn(g0.w) * (s.p - c);
+    float3 outward = rcp_fast(g0.w) * (s.p - c);
     s.p = fma3(g0.w, outward, c);  // re-project onto the sphere: removes the O(t*eps) drift of o + t d
     s.material = meta.x;
     float4 m1 = __ldg(sc.materials + 2 * meta.x + 1);
@@ -745,7 +748,7 @@ __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface
     }
     case MAT_DIELECTRIC: {  // material.hpp:128-206
       atten = f3(1.0f, 1.0f, 1.0f);
-      float ri = s.front ? __frcp_rn(m0.w) : m0.w;
+      float ri = s.front ? rcp_fast(m0.w) : m0.w;
       float3 ud = normalize3(d_in);
       float cos_t = fminf(-dot(ud, s.n), 1.0f);
       float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));

@@ -301,8 +301,8 @@ __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, fl
           tslot = tq[(tq_head + rank) & QM];
           const float3 o = f3(PF(PF_OX, tslot), PF(PF_OY, tslot), PF(PF_OZ, tslot));
           const float3 d = f3(PF(PF_DX, tslot), PF(PF_DY, tslot), PF(PF_DZ, tslot));
-          const float3 inv = f3(fabsf(d.x) > 1e-30f ? __frcp_rn(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? __frcp_rn(d.y) : copysignf(1e30f, d.y),
-                                fabsf(d.z) > 1e-30f ? __frcp_rn(d.z) : copysignf(1e30f, d.z));
+          const float3 inv = f3(fabsf(d.x) > 1e-30f ? rcp_fast(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? rcp_fast(d.y) : copysignf(1e30f, d.y),
+                                fabsf(d.z) > 1e-30f ? rcp_fast(d.z) : copysignf(1e30f, d.z));
           const float3 ood = o * inv;
           lsc[0] = make_float4(inv.x, inv.y, inv.z, ood.x);
           lsc[32] = make_float4(ood.y, ood.z, 0.0f, 0.0f);
