@@ -179,8 +179,9 @@ __device__ __forceinline__ bool box_slabs(float4 b0, float4 b1, float4 b2, float
     z0 = fmaf(b0.z, inv.z, -ood.z), z1 = fmaf(b1.z, inv.z, -ood.z);
   }
   if (self_face >= 0) {  // a ray that starts ON that face of this box crosses its plane at exactly 0: no fp32 epsilon
-    if (self_face == 0) x0 = 0.0f; else if (self_face == 1) x1 = 0.0f; else if (self_face == 2) y0 = 0.0f;
-    else if (self_face == 3) y1 = 0.0f; else if (self_face == 4) z0 = 0.0f; else z1 = 0.0f;
+    x0 = self_face == 0 ? 0.0f : x0, x1 = self_face == 1 ? 0.0f : x1;  // selects, not a jump table
+    y0 = self_face == 2 ? 0.0f : y0, y1 = self_face == 3 ? 0.0f : y1;
+    z0 = self_face == 4 ? 0.0f : z0, z1 = self_face == 5 ? 0.0f : z1;
   }
   r.nx = fminf(x0, x1), r.ny = fminf(y0, y1), r.nz = fminf(z0, z1);
   r.fx = fmaxf(x0, x1), r.fy = fmaxf(y0, y1), r.fz = fmaxf(z0, z1);
@@ -227,11 +228,19 @@ struct NodeSource {
   const float4* gmem;
   int smem_nodes;
 };
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
   float4 dd;
   if (idx < ns.smem_nodes) {
-    const float4* p = ns.smem + 4 * idx;
-    a = p[0], b = p[1], c = p[2], dd = p[3];
+    // 32-bit shared-window address: through the generic pointer the compiler rebuilt the window base
+    // (S2R CgaCtaId, MOV, LEA, LEA) at every node step
+    const uint32_t p = uint32_t(__cvta_generic_to_shared(ns.smem)) + 64u * uint32_t(idx);
+    a = lds_f4(p), b = lds_f4(p + 16u), c = lds_f4(p + 32u);
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dd.x), "=f"(dd.y) : "r"(p + 48u));
   } else {
     const float4* p = ns.gmem + 4 * idx;
     a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), dd = __ldg(p + 3);
@@ -521,6 +530,14 @@ __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const
   TravStack st;
   int mode = MODE_DONE;
   if (active) ts.sp = 0, ts.cur = 0, mode = MODE_NODE;
+#if RT_NODE_THR == 1
+  for (;;) {  // while-while: node steps while ANY lane wants one (one vote per step), then one leaf step for the rest
+    while (__any_sync(FULL, mode == MODE_NODE))
+      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    if (!__any_sync(FULL, mode == MODE_LEAF)) break;
+    if (mode == MODE_LEAF) mode = leaf_step<COUNT, CALLFREE>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+  }
+#else
   for (;;) {
     const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF);
     if ((bN | bL) == 0u) break;
@@ -530,6 +547,7 @@ __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const
       if (mode == MODE_LEAF) mode = leaf_step<COUNT, CALLFREE>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
     }
   }
+#endif
   return ts.best;
 }
 
@@ -559,17 +577,25 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
   int mode = MODE_DONE;
   ts.best = Hit{tmax, REF_NONE};
   if (active) mode = trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
+#if RT_NODE_THR == 1
+  for (;;) {  // classic while-while: the node loop drains to the last lane (one vote per step), then the leaves
+    while (__any_sync(FULL, mode == MODE_NODE))
+      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+    if (!__any_sync(FULL, mode == MODE_LEAF)) break;
+    if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+  }
+#else
   for (;;) {
     const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF);
     if ((bN | bL) == 0u) break;
-    // node steps while at least RT_NODE_THR lanes want one (RT_NODE_THR == 1: classic while-while,
-    // the inner loop drains to the last lane); below the threshold the lanes waiting on leaves go first
+    // node steps while at least RT_NODE_THR lanes want one; below the threshold the lanes waiting on leaves go first
     if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
       if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
     } else {
       if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
     }
   }
+#endif
   return ts.best;
 }
 
