@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
 #endif
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
   __syncthreads();
-  const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
+  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
 
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
   extern __shared__ float4 s_nodes[];
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
   __syncthreads();
-  const NodeSource ns{s_nodes, P.sc.nodes, P.smem_nodes};
+  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
   const DeviceScene& sc = P.sc;

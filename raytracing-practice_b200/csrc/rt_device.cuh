@@ -227,7 +227,15 @@ struct NodeSource {
   const float4* smem;
   const float4* gmem;
   int smem_nodes;
+  uint32_t smem_addr;  // 32-bit shared-window address of `smem`, see node_source()
 };
+// The shared address is laundered through an opaque mov so that it LIVES IN A REGISTER: left to itself the compiler
+// rebuilds it (S2R CgaCtaId, MOV, LEA, IMAD) at every node step.
+__device__ __forceinline__ NodeSource node_source(const float4* smem, const float4* gmem, int smem_nodes) {
+  uint32_t a = uint32_t(__cvta_generic_to_shared(smem));
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));
+  return NodeSource{smem, gmem, smem_nodes, a};
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -238,7 +246,7 @@ __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4&
   if (idx < ns.smem_nodes) {
     // 32-bit shared-window address: through the generic pointer the compiler rebuilt the window base
     // (S2R CgaCtaId, MOV, LEA, LEA) at every node step
-    const uint32_t p = uint32_t(__cvta_generic_to_shared(ns.smem)) + 64u * uint32_t(idx);
+    const uint32_t p = ns.smem_addr + 64u * uint32_t(idx);
     a = lds_f4(p), b = lds_f4(p + 16u), c = lds_f4(p + 32u);
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dd.x), "=f"(dd.y) : "r"(p + 48u));
   } else {
@@ -563,7 +571,7 @@ __device__ __noinline__ Hit closest_hit_outlined(const DeviceScene* __restrict__
   TravState ts;
   trav_set_ray(ts, o, d, time, 0.001f, skip);
   ts.best = best;
-  const NodeSource ns{s_nodes, sc->nodes, smem_nodes};
+  const NodeSource ns = node_source(s_nodes, sc->nodes, smem_nodes);
   const PathKey key{seed, pixel, sample};
   return closest_hit_prepared<COUNT, true>(*sc, ns, ts, sc->n_media != 0, key, bounce, cn, active);
 }

@@ -269,7 +269,7 @@ __device__ __noinline__ void trace_phase(const RenderParams* __restrict__ Pp, fl
   const DeviceScene& sc = P.sc;
   const unsigned FULL = 0xFFFFFFFFu;
   const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-  const NodeSource ns{s_nodes, sc.nodes, P.smem_nodes};
+  const NodeSource ns = node_source(s_nodes, sc.nodes, P.smem_nodes);
   const bool media = sc.n_media != 0;
   unsigned char* const tq = reinterpret_cast<unsigned char*>(pool + kPoolQueueOff);
   unsigned char* const sq = tq + NP;
