@@ -70,7 +70,7 @@ __device__ __forceinline__ long long to_fixed(float v) {
   return __float2ll_rn(v * kFixScale);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool ALL_SMEM>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
 #if RT_OUTLINED_TRAVERSAL
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     if (alive && media) h = sample_global_media<COUNT>(sc, o, d, time, 0.001f, INF, key, bounce, cn);
     h = closest_hit_outlined<COUNT>(&s_sc, s_nodes, P.smem_nodes, o, d, time, skip, h, P.key, key.pixel, key.sample, bounce, alive, cn);
 #else
-    Hit h = closest_hit<COUNT>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive);
+    Hit h = closest_hit<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive);
 #endif
     if (alive) {
       if (h.ref == REF_NONE) {
@@ -821,14 +821,16 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
       pool_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
     ctx->launches++;
   } else {
-    RT_CUDA(ctx, cudaFuncSetAttribute(count ? render_kernel<true> : render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    // the kernel is specialised for "the whole BVH is staged in shared memory" (all BASELINE scenes): its node step
+    // then has neither the bounds test nor the global-memory path
+    const bool all_smem = P.smem_nodes >= ctx->sc.n_nodes;
+    void (*kern)(RenderParams) = count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
+                                       : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
+    RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // counters[0] = first item not pre-assigned to a thread
     unsigned long long first = (unsigned long long)threads;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
-    if (count)
-      render_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
-    else
-      render_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    kern<<<grid, kRenderThreads, smem, ctx->stream>>>(P);
     ctx->launches++;
   }
   ctx->samples_total += (unsigned long long)f.image_width * f.image_height * P.sample_count;

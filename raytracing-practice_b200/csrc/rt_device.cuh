@@ -241,9 +241,10 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+template <bool ALL_SMEM = false>
 __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
   float4 dd;
-  if (idx < ns.smem_nodes) {
+  if (ALL_SMEM || idx < ns.smem_nodes) {
     // 32-bit shared-window address: through the generic pointer the compiler rebuilt the window base
     // (S2R CgaCtaId, MOV, LEA, LEA) at every node step
     const uint32_t p = ns.smem_addr + 64u * uint32_t(idx);
@@ -352,6 +353,9 @@ __device__ RT_OUTLINE float medium_sample(const DeviceScene& sc, const DMedium& 
 }
 
 constexpr int kStackDepth = 32;
+// TravState::cur of a finished (or idle) traversal: negative like a leaf code, but no leaf code can have this value
+// (it would need 2^28 leaf references).  Lets a loop read the lane's mode off `cur` alone: >= 0 node, else leaf / done.
+constexpr int kTravDone = int(0x80000000u);
 #ifndef RT_NODE_THR
 #define RT_NODE_THR 1
 #endif
@@ -392,6 +396,7 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
       return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
     }
   }
+  ts.cur = kTravDone;
   return MODE_SHADE;  // traversal finished: ts.best is the answer
 }
 
@@ -443,11 +448,11 @@ __device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, 
   return MODE_NODE;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool ALL_SMEM = false>
 __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const NodeSource& ns, unsigned int* cn) {
   float4 a, b, c;
   int c0, c1;
-  load_node(ns, ts.cur, a, b, c, c0, c1);
+  load_node<ALL_SMEM>(ns, ts.cur, a, b, c, c0, c1);
   if (COUNT) cn[CN_NODE]++;
   const float3 inv = ts.inv, ood = ts.ood;
   // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
@@ -464,11 +469,11 @@ __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const Nod
   const bool h0 = n0 <= f0, h1 = n1 <= f1;
   if (h0 && h1) {  // near child first, far child on the stack with its entry distance
     const bool first0 = n0 <= n1;
-    if (ts.sp < kStackDepth) {
-      st.node[ts.sp] = first0 ? c1 : c0;
-      st.t[ts.sp] = first0 ? n1 : n0;
-      ts.sp++;
-    }
+    // no overflow guard: rt_upload_scene rejects a BVH deeper than kStackDepth, and the stack never holds more
+    // entries than the tree has levels
+    st.node[ts.sp] = first0 ? c1 : c0;
+    st.t[ts.sp] = first0 ? n1 : n0;
+    ts.sp++;
     ts.cur = first0 ? c0 : c1;
     return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
   }
@@ -576,29 +581,33 @@ __device__ __noinline__ Hit closest_hit_outlined(const DeviceScene* __restrict__
   return closest_hit_prepared<COUNT, true>(*sc, ns, ts, sc->n_media != 0, key, bounce, cn, active);
 }
 
-template <bool COUNT>
+// ALL_SMEM: every BVH node is staged in shared memory (true for all the BASELINE scenes): no bounds test, no global path
+template <bool COUNT, bool ALL_SMEM = false>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
                                            uint32_t skip_ref, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn, bool active = true) {
   const unsigned FULL = 0xFFFFFFFFu;
   TravState ts;
   TravStack st;
-  int mode = MODE_DONE;
   ts.best = Hit{tmax, REF_NONE};
-  if (active) mode = trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
+  ts.cur = kTravDone;
+  if (active) trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
 #if RT_NODE_THR == 1
-  for (;;) {  // classic while-while: the node loop drains to the last lane (one vote per step), then the leaves
-    while (__any_sync(FULL, mode == MODE_NODE))
-      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
-    if (!__any_sync(FULL, mode == MODE_LEAF)) break;
-    if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+  // classic while-while with the lane's mode read off ts.cur (>= 0: node, kTravDone: finished, else a leaf): the
+  // node loop drains to the last lane — one vote per step —, then the leaves are intersected together
+  for (;;) {
+    while (__any_sync(FULL, ts.cur >= 0))
+      if (ts.cur >= 0) node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
+    if (!__any_sync(FULL, ts.cur != kTravDone)) break;
+    if (ts.cur != kTravDone) leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
   }
 #else
+  int mode = active ? MODE_NODE : MODE_DONE;
   for (;;) {
     const unsigned bN = __ballot_sync(FULL, mode == MODE_NODE), bL = __ballot_sync(FULL, mode == MODE_LEAF);
     if ((bN | bL) == 0u) break;
     // node steps while at least RT_NODE_THR lanes want one; below the threshold the lanes waiting on leaves go first
     if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
-      if (mode == MODE_NODE) mode = node_step<COUNT>(ts, st, ns, cn);
+      if (mode == MODE_NODE) mode = node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
     } else {
       if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
     }

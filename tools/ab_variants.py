@@ -16,7 +16,7 @@ if sys.argv[1] == "build":
     for tag, p in procs:
         err = p.communicate()[1]
         regs = [l for l in err.splitlines() if "Used" in l]
-        k = [i for i, l in enumerate(err.splitlines()) if "render_kernelILb0" in l and "Compiling" in l]
+        k = [i for i, l in enumerate(err.splitlines()) if "render_kernelILb0ELb1" in l and "Compiling" in l]
         info = err.splitlines()[k[0] + 2].strip() if k else "?"
         spill = err.splitlines()[k[0] + 1 + 1 - 1].strip() if k else ""
         print(tag, p.returncode, info, "|", [l.strip() for l in err.splitlines()[k[0]+1:k[0]+3]][0] if k else "")
