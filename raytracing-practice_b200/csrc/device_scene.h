@@ -91,7 +91,7 @@ struct DeviceScene {
   const XQuad* xquads;
   const XOp* xops;
   const int2* xchains;  // {first op, n ops}
-  int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures, n_boxes;
+  int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures, n_boxes, n_leaf_refs;
   int n_global_media;   // media that enclose the whole scene: sampled once per ray, not via the BVH
   int global_media[4];
   float scene_abs_max;  // max |coordinate| of any finite bound (conservative-cull epsilon scale)

@@ -78,6 +78,18 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   for (int i = threadIdx.x; i < int(sizeof(DeviceScene) / 4); i += blockDim.x) reinterpret_cast<int*>(&s_sc)[i] = reinterpret_cast<const int*>(&P.sc)[i];
 #endif
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
+  LeafSource ls{0u, 0u, 0u};
+  if (ALL_SMEM) {  // ... and the leaves' data: [nodes][spheres 2 x float4][boxes 3 x float4][leaf refs u32]
+    float4* s_sph = s_nodes + 4 * P.smem_nodes;
+    float4* s_box = s_sph + 2 * P.sc.n_spheres;
+    uint32_t* s_ref = reinterpret_cast<uint32_t*>(s_box + 3 * P.sc.n_boxes);
+    for (int i = threadIdx.x; i < 2 * P.sc.n_spheres; i += blockDim.x) s_sph[i] = P.sc.spheres[i];
+    for (int i = threadIdx.x; i < 3 * P.sc.n_boxes; i += blockDim.x) s_box[i] = P.sc.boxes[i];
+    for (int i = threadIdx.x; i < P.sc.n_leaf_refs; i += blockDim.x) s_ref[i] = P.sc.leaf_refs[i];
+    ls.spheres = opaque_u32(uint32_t(__cvta_generic_to_shared(s_sph)));
+    ls.boxes = opaque_u32(uint32_t(__cvta_generic_to_shared(s_box)));
+    ls.refs = opaque_u32(uint32_t(__cvta_generic_to_shared(s_ref)));
+  }
   __syncthreads();
   const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
   const DeviceScene& sc = P.sc;
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     if (alive && media) h = sample_global_media<COUNT>(sc, o, d, time, 0.001f, INF, key, bounce, cn);
     h = closest_hit_outlined<COUNT>(&s_sc, s_nodes, P.smem_nodes, o, d, time, skip, h, P.key, key.pixel, key.sample, bounce, alive, cn);
 #else
-    Hit h = closest_hit<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive);
+    Hit h = closest_hit<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive, ls);
 #endif
     if (alive) {
       if (h.ref == REF_NONE) {
@@ -699,6 +711,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.n_spheres = int(h.spheres.size() / 2);
   s.n_quads = int(h.quads.size() / 3);
   s.n_boxes = int(h.boxes.size() / 3);
+  s.n_leaf_refs = int(h.leaf_refs.size());
   s.n_media = int(h.media.size());
   s.n_materials = int(h.materials.size() / 2);
   s.n_textures = int(h.textures.size() / 2);
@@ -821,9 +834,12 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
       pool_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
     ctx->launches++;
   } else {
-    // the kernel is specialised for "the whole BVH is staged in shared memory" (all BASELINE scenes): its node step
-    // then has neither the bounds test nor the global-memory path
-    const bool all_smem = P.smem_nodes >= ctx->sc.n_nodes;
+    // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared
+    // memory" (all BASELINE scenes): its node step then has neither the bounds test nor the global-memory path, and a
+    // leaf visit makes no global load
+    const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
+    const bool all_smem = staged + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+    if (all_smem) P.smem_nodes = ctx->sc.n_nodes, smem = staged;
     void (*kern)(RenderParams) = count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
                                        : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
     RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -241,6 +241,22 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// Leaf data staged in shared memory next to the nodes (kernels specialised with ALL_SMEM): 32-bit shared-window
+// addresses of copies of leaf_refs / spheres / boxes.  A leaf visit then makes no global load at all (quads and media,
+// rare as leaf items, still go to global memory), and the reference -> primitive chain is two LDS, not two LDG.
+struct LeafSource {
+  uint32_t refs, spheres, boxes;
+};
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t a) {  // keeps a shared address in a register (see node_source)
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));
+  return a;
+}
+
 template <bool ALL_SMEM = false>
 __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
   float4 dd;
@@ -486,17 +502,20 @@ __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const Nod
 
 // leaf: ~cur = (first << 3) | (count - 1)
 // `key_of(key, bounce)` yields the ray's Philox counter; it is only called when a medium is actually sampled
-template <bool COUNT, bool CALLFREE = false, typename KeyFn>
-__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn) {
+template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn>
+__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
+                                         const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
   const int code = ~ts.cur;
   const int first = code >> 3, count = (code & 7) + 1;
   const float3 o = ts.o, d = ts.d;
   for (int k = 0; k < count; k++) {
-    uint32_t ref = __ldg(sc.leaf_refs + first + k);
+    uint32_t ref = STAGED ? lds_u32(ls.refs + 4u * uint32_t(first + k)) : __ldg(sc.leaf_refs + first + k);
     uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
     float t = -1.0f;
     if (type == REF_SPHERE) {
-      t = hit_sphere(__ldg(sc.spheres + 2 * idx), __ldg(sc.spheres + 2 * idx + 1), o, d, ts.time, ts.tmin, ts.best.t, ref == ts.skip);
+      const float4 g0 = STAGED ? lds_f4(ls.spheres + 32u * idx) : __ldg(sc.spheres + 2 * idx);
+      const float4 g1 = STAGED ? lds_f4(ls.spheres + 32u * idx + 16u) : __ldg(sc.spheres + 2 * idx + 1);
+      t = hit_sphere(g0, g1, o, d, ts.time, ts.tmin, ts.best.t, ref == ts.skip);
       if (COUNT) cn[CN_SPH]++, cn[CN_SPH_HIT] += t != -1.0f;
     } else if (type == REF_QUAD) {
       if (ref != ts.skip) {
@@ -512,7 +531,10 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
         const uint32_t b = idx >> 3;
         const int self_face = ((ts.skip >> 30) == REF_BOX && ts.skip != REF_NONE && ((ts.skip & 0x3FFFFFFFu) >> 3) == b) ? int(ts.skip & 7u) : -1;
         int face = 0;
-        t = hit_box(__ldg(sc.boxes + 3 * b), __ldg(sc.boxes + 3 * b + 1), __ldg(sc.boxes + 3 * b + 2), o, d, ts.inv, ts.ood, ts.tmin, ts.best.t, self_face, face);
+        const float4 b0 = STAGED ? lds_f4(ls.boxes + 48u * b) : __ldg(sc.boxes + 3 * b);
+        const float4 b1 = STAGED ? lds_f4(ls.boxes + 48u * b + 16u) : __ldg(sc.boxes + 3 * b + 1);
+        const float4 b2 = STAGED ? lds_f4(ls.boxes + 48u * b + 32u) : __ldg(sc.boxes + 3 * b + 2);
+        t = hit_box(b0, b1, b2, o, d, ts.inv, ts.ood, ts.tmin, ts.best.t, self_face, face);
         if (COUNT) cn[CN_BOX]++;
         ref = make_ref(REF_BOX, (b << 3) | uint32_t(face));
       }
@@ -584,7 +606,8 @@ __device__ __noinline__ Hit closest_hit_outlined(const DeviceScene* __restrict__
 // ALL_SMEM: every BVH node is staged in shared memory (true for all the BASELINE scenes): no bounds test, no global path
 template <bool COUNT, bool ALL_SMEM = false>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
-                                           uint32_t skip_ref, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn, bool active = true) {
+                                           uint32_t skip_ref, bool media, const PathKey& key, uint32_t bounce, unsigned int* cn, bool active = true,
+                                           const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
   const unsigned FULL = 0xFFFFFFFFu;
   TravState ts;
   TravStack st;
@@ -598,7 +621,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
     while (__any_sync(FULL, ts.cur >= 0))
       if (ts.cur >= 0) node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
     if (!__any_sync(FULL, ts.cur != kTravDone)) break;
-    if (ts.cur != kTravDone) leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+    if (ts.cur != kTravDone) leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn, ls);
   }
 #else
   int mode = active ? MODE_NODE : MODE_DONE;
@@ -609,7 +632,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
     if (__popc(bN) >= RT_NODE_THR || bL == 0u) {
       if (mode == MODE_NODE) mode = node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
     } else {
-      if (mode == MODE_LEAF) mode = leaf_step<COUNT>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn);
+      if (mode == MODE_LEAF) mode = leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn, ls);
     }
   }
 #endif
