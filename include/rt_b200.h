@@ -203,6 +203,11 @@ typedef struct rt_render_opts {
   void* peer_accum;     /* optional: device pointer (own or peer-mapped over NVLink) of
                            another context's accumulator; when non-NULL the kernel adds
                            its samples THERE (red.add.u64) instead of locally          */
+  void* push_accum;     /* optional: a reduce buffer (rt_reduce_buffer of this or another
+                           rank, peer-mapped over NVLink): the render kernel accumulates
+                           locally and, once its last CTA has finished, ADDS its whole
+                           accumulator into that buffer (system-scope red.add.u64) — the
+                           multi-GPU reduce fused into the render kernel's epilogue     */
 } rt_render_opts;
 
 enum {
@@ -222,6 +227,20 @@ int rt_synchronize(rt_ctx* ctx);
 /* The accumulator (3 x int64 per pixel, row-major from the top-left, interleaved RGB)
  * as a raw device pointer, for the multi-GPU reduce (NCCL ncclInt64 sum, or peer adds). */
 int rt_accum_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
+
+/* ---- fused multi-GPU reduce (the exchange step of camera.hpp:61,65 without a collective call) ----
+ * Rank 0 allocates a zeroed reduce buffer (same layout as the accumulator) and exports it; the other
+ * ranks (processes) open it through CUDA IPC / peer access; every rank renders its sample shard with
+ * rt_render_opts.push_accum pointing at it; after a barrier rank 0 adopts the buffer as its image.   */
+typedef struct rt_ipc_handle {
+  unsigned char bytes[64]; /* cudaIpcMemHandle_t */
+} rt_ipc_handle;
+int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_ipc_handle* handle /* may be NULL */);
+int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr);
+int rt_peer_close(rt_ctx* ctx, void* dev_ptr);
+/* Copies the reduce buffer over the context's accumulator (rt_download / rt_accum_device_ptr then read the
+ * reduced image).  The buffer and its handle stay valid: rt_reduce_buffer with the same camera re-zeroes it. */
+int rt_adopt_reduce_buffer(rt_ctx* ctx);
 
 typedef enum rt_buffer_kind {
   RT_BUF_ACCUM_I64 = 0,    /* raw fixed-point sums, 3 x int64 per pixel                */

@@ -53,6 +53,10 @@ def cuda_lib():
         lib.rt_render.argtypes = [C.c_void_p, C.POINTER(_abi.rt_camera_desc), C.POINTER(_abi.rt_render_opts)]
         lib.rt_synchronize.argtypes = [C.c_void_p]
         lib.rt_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        lib.rt_reduce_buffer.argtypes = [C.c_void_p, C.POINTER(_abi.rt_camera_desc), C.POINTER(C.c_void_p), C.POINTER(_abi.rt_ipc_handle)]
+        lib.rt_peer_open.argtypes = [C.c_void_p, C.POINTER(_abi.rt_ipc_handle), C.POINTER(C.c_void_p)]
+        lib.rt_peer_close.argtypes = [C.c_void_p, C.c_void_p]
+        lib.rt_adopt_reduce_buffer.argtypes = [C.c_void_p]
         lib.rt_download.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_size_t]
         lib.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.rt_stats)]
         lib.rt_camera_initialize.argtypes = [C.POINTER(_abi.rt_camera_desc), C.POINTER(_abi.rt_camera_frame)]
@@ -166,9 +170,28 @@ class Context:
     def upload_scene(self, desc):
         self._check(self._lib.rt_upload_scene(self._h, desc), "rt_upload_scene")
 
-    def render(self, cam, seed=0, sample_begin=0, sample_count=0, clear=True, peer_accum=None, flags=0):
-        o = _abi.rt_render_opts(seed, sample_begin, sample_count, 1 if clear else 0, flags, peer_accum)
+    def render(self, cam, seed=0, sample_begin=0, sample_count=0, clear=True, peer_accum=None, flags=0, push_accum=None):
+        o = _abi.rt_render_opts(seed, sample_begin, sample_count, 1 if clear else 0, flags, peer_accum, push_accum)
         self._check(self._lib.rt_render(self._h, C.byref(cam), C.byref(o)), "rt_render")
+
+    def reduce_buffer(self, cam):
+        """Allocate / zero this context's reduce buffer for `cam`; returns (device pointer, 64-byte IPC handle)."""
+        p, h = C.c_void_p(), _abi.rt_ipc_handle()
+        self._check(self._lib.rt_reduce_buffer(self._h, C.byref(cam), C.byref(p), C.byref(h)), "rt_reduce_buffer")
+        return p.value, bytes(h.bytes)
+
+    def peer_open(self, handle_bytes):
+        h = _abi.rt_ipc_handle()
+        C.memmove(h.bytes, handle_bytes, 64)
+        p = C.c_void_p()
+        self._check(self._lib.rt_peer_open(self._h, C.byref(h), C.byref(p)), "rt_peer_open")
+        return p.value
+
+    def peer_close(self, ptr):
+        self._check(self._lib.rt_peer_close(self._h, ptr), "rt_peer_close")
+
+    def adopt_reduce_buffer(self):
+        self._check(self._lib.rt_adopt_reduce_buffer(self._h), "rt_adopt_reduce_buffer")
 
     def synchronize(self):
         self._check(self._lib.rt_synchronize(self._h), "rt_synchronize")

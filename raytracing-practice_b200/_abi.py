@@ -132,7 +132,12 @@ class rt_render_opts(C.Structure):
         ("clear", C.c_int32),
         ("flags", C.c_int32),
         ("peer_accum", C.c_void_p),
+        ("push_accum", C.c_void_p),
     ]
+
+
+class rt_ipc_handle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
 class rt_stats(C.Structure):
@@ -164,6 +169,10 @@ C_ABI_SYMBOLS = [
     "rt_render",
     "rt_synchronize",
     "rt_accum_device_ptr",
+    "rt_reduce_buffer",
+    "rt_peer_open",
+    "rt_peer_close",
+    "rt_adopt_reduce_buffer",
     "rt_download",
     "rt_get_stats",
     "rt_trace_rays",

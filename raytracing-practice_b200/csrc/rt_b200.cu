@@ -42,6 +42,8 @@ struct RenderParams {
   unsigned int per_chunk;  // work items per sample chunk = tiles_x * tiles_y * 32
   unsigned int n_items;
   unsigned long long* accum;     // 3 x int64 per pixel (two's complement adds)
+  unsigned long long* push;      // fused reduce: a reduce buffer (possibly another GPU's) the epilogue adds `accum` into
+  unsigned long long n_values;   // 3 * W * H
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
   float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
@@ -68,6 +70,29 @@ __device__ __forceinline__ long long to_fixed(float v) {
   // NaN -> 0 (a NaN sample would poison the pixel); clamp keeps 2^31 samples from overflowing
   v = (v == v) ? fminf(fmaxf(v, 0.0f), 1.0e6f) : 0.0f;
   return __float2ll_rn(v * kFixScale);
+}
+
+// The multi-GPU exchange step (the per-pixel sum of camera.hpp:61 across ranks) FUSED into the render kernel: once
+// every CTA of this launch has finished accumulating (a grid-wide arrival counter; the grid is one persistent CTA
+// per SM, so spinning on it is safe), each CTA adds its slice of the local accumulator into the reduce buffer —
+// rank 0's own memory or another GPU's, peer-mapped over NVLink — with system-scope red.add.u64.  Integer adds
+// commute, so the reduced image has the same bits as a single-GPU render; no collective call, no second kernel.
+__device__ __forceinline__ void push_accumulator(const RenderParams& P) {
+  if (P.push == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(P.counters + 3, 1ull);
+    while (*reinterpret_cast<volatile unsigned long long*>(P.counters + 3) < (unsigned long long)gridDim.x) __nanosleep(200);
+    __threadfence();
+  }
+  __syncthreads();
+  const unsigned long long per = (P.n_values + gridDim.x - 1) / gridDim.x;
+  const unsigned long long begin = per * blockIdx.x, end = min(begin + per, P.n_values);
+  for (unsigned long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const unsigned long long v = __ldcg(P.accum + i);  // L2: the sums were made by red.add at L2
+    if (v) atomicAdd_system(P.push + i, v);
+  }
 }
 
 template <bool COUNT, bool ALL_SMEM>
@@ -217,6 +242,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   unsigned int rays = n_rays;
   for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
   if ((threadIdx.x & 31) == 0) atomicAdd(P.counters + 1, (unsigned long long)rays);
+  push_accumulator(P);
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++)
       if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);
@@ -475,6 +501,10 @@ struct rt_ctx {
   int smem_nodes = 0;
   int launches = 0;
   void* pool_cold = nullptr;  // pool kernel, RT_POOL_COLD_GLOBAL builds only
+  void* scratch = nullptr;  // rt_download's device-side staging buffer
+  size_t scratch_bytes = 0;
+  unsigned long long* reduce_buf = nullptr;  // fused multi-GPU reduce: peers add their accumulators here
+  size_t reduce_values = 0;
 };
 
 #define RT_CUDA(ctx, call)                                                                          \
@@ -655,6 +685,8 @@ void rt_shutdown(rt_ctx* ctx) {
   free_scene(ctx);
   cudaFree(ctx->accum);
   cudaFree(ctx->pool_cold);
+  cudaFree(ctx->reduce_buf);
+  cudaFree(ctx->scratch);
   cudaFree(ctx->counters);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -795,6 +827,10 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   P.per_chunk = unsigned(P.tiles_x) * unsigned(P.tiles_y) * 32u;
   P.n_items = unsigned(n_items);
   P.accum = opts->peer_accum ? static_cast<unsigned long long*>(opts->peer_accum) : ctx->accum;
+  P.push = static_cast<unsigned long long*>(opts->push_accum);
+  P.n_values = (unsigned long long)f.image_width * f.image_height * 3ull;
+  if (P.push && opts->peer_accum) return fail(ctx, RT_ERR_INVALID, "peer_accum and push_accum are mutually exclusive");
+  if (P.push) RT_CUDA(ctx, cudaMemsetAsync(ctx->counters + 3, 0, sizeof(unsigned long long), ctx->stream));  // the epilogue's arrival counter
   P.counters = ctx->counters;
   P.smem_nodes = ctx->smem_nodes;
   size_t smem = size_t(P.smem_nodes) * 64;
@@ -871,6 +907,63 @@ int rt_accum_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes) {
   return RT_OK;
 }
 
+// ---- fused multi-GPU reduce: a reduce buffer other ranks' render kernels add their accumulators into ----------
+int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_ipc_handle* handle) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!cam || !dev_ptr || cam->image_width <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera / null output");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  rt_camera_frame f;
+  rt_camera_initialize(cam, &f);
+  const size_t values = size_t(f.image_width) * f.image_height * 3;
+  if (values != ctx->reduce_values) {
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->reduce_buf);
+  cudaFree(ctx->scratch);
+    ctx->reduce_buf = nullptr, ctx->reduce_values = 0;
+    RT_CUDA(ctx, cudaMalloc(&ctx->reduce_buf, values * 8));
+    ctx->reduce_values = values;
+  }
+  RT_CUDA(ctx, cudaMemsetAsync(ctx->reduce_buf, 0, values * 8, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // zeroed before any peer may add into it
+  *dev_ptr = ctx->reduce_buf;
+  if (handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(rt_ipc_handle), "rt_ipc_handle must hold a cudaIpcMemHandle_t");
+    cudaIpcMemHandle_t h;
+    RT_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->reduce_buf));
+    std::memcpy(handle->bytes, &h, sizeof h);
+  }
+  return RT_OK;
+}
+
+int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!handle || !dev_ptr) return fail(ctx, RT_ERR_INVALID, "null handle / output");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle->bytes, sizeof h);
+  RT_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RT_OK;
+}
+
+int rt_peer_close(rt_ctx* ctx, void* dev_ptr) {
+  if (!ctx) return RT_ERR_INVALID;
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RT_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+  return RT_OK;
+}
+
+int rt_adopt_reduce_buffer(rt_ctx* ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->reduce_buf) return fail(ctx, RT_ERR_INVALID, "no reduce buffer (call rt_reduce_buffer first)");
+  if (ctx->reduce_values != ctx->accum_values || !ctx->accum) return fail(ctx, RT_ERR_INVALID, "reduce buffer and accumulator differ in size");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  // a copy, not a pointer swap: the reduce buffer (and its IPC handle, which peers keep open) stays where it is
+  RT_CUDA(ctx, cudaMemcpyAsync(ctx->accum, ctx->reduce_buf, ctx->accum_values * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
 int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t bytes) {
   if (!ctx) return RT_ERR_INVALID;
   if (!dst) return fail(ctx, RT_ERR_INVALID, "null destination");
@@ -888,8 +981,15 @@ int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t
   if (!f32 && kind != RT_BUF_RGB8) return fail(ctx, RT_ERR_INVALID, "unknown buffer kind");
   const size_t need = f32 ? n * 4 : n;
   if (bytes < need) return fail(ctx, RT_ERR_INVALID, "destination too small");
-  void* tmp = nullptr;
-  RT_CUDA(ctx, cudaMalloc(&tmp, need));
+  // persistent scratch: with peer access enabled (NCCL, CUDA IPC) every cudaMalloc / cudaFree also updates the peers'
+  // mappings and costs tens of milliseconds
+  if (need > ctx->scratch_bytes) {
+    cudaFree(ctx->scratch);
+    ctx->scratch = nullptr, ctx->scratch_bytes = 0;
+    RT_CUDA(ctx, cudaMalloc(&ctx->scratch, need));
+    ctx->scratch_bytes = need;
+  }
+  void* tmp = ctx->scratch;
   const double scale = double(1.0f / float(spp));  // pixel_samples_scale, camera.hpp:83
   finalize_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const long long*>(ctx->accum), (long long)n, scale,
                                                                       f32 ? static_cast<float*>(tmp) : nullptr,
@@ -898,7 +998,6 @@ int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, need, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(tmp);
   if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, std::string("rt_download: ") + cudaGetErrorString(e));
   return RT_OK;
 }

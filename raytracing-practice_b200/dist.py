@@ -63,3 +63,54 @@ def render_sharded(ctx, cam, seed=0):
     if world > 1:
         reduce_accum_to_rank0(ctx.accum_tensor())
         torch.cuda.synchronize()
+
+
+class FusedReduce:
+    """The exchange step without a collective call: rank 0 owns a reduce buffer, every rank's render kernel adds its
+    accumulator into it from its epilogue (rt_render_opts.push_accum: system-scope red.add.u64 over NVLink peer memory
+    for the other ranks).  torch.distributed only ships the 64-byte IPC handle once and provides the barriers."""
+
+    def __init__(self, ctx, cam):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.cam = ctx, cam
+        self.rank, _, self.world = env_rank()
+        self.multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        if self.rank == 0:
+            self.ptr, handle = ctx.reduce_buffer(cam)
+        else:
+            handle = bytes(64)
+        if self.multi:
+            dev = f"cuda:{ctx.device}" if torch.cuda.is_available() else "cpu"
+            t = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0)
+            if self.rank != 0:
+                self.ptr = ctx.peer_open(bytes(t.cpu().tolist()))
+
+    def render(self, seed=0):
+        """One frame: zero the buffer (rank 0), barrier, every rank renders its shard and pushes, barrier, rank 0 adopts."""
+        import torch
+        import torch.distributed as dist
+
+        begin, count = shard_samples(self.cam.samples_per_pixel, self.rank, self.world)
+        if self.rank == 0:
+            self.ctx.reduce_buffer(self.cam)  # re-zero, same pointer
+        if self.multi:
+            dist.barrier()
+        if count > 0:
+            self.ctx.render(self.cam, seed=seed, sample_begin=begin, sample_count=count, clear=True, push_accum=self.ptr)
+        self.ctx.synchronize()
+        if self.multi:
+            dist.barrier()
+        self.adopt_ms = 0.0
+        if self.rank == 0:
+            import time
+
+            t0 = time.time()
+            self.ctx.adopt_reduce_buffer()
+            self.adopt_ms = (time.time() - t0) * 1e3
+
+    def close(self):
+        if self.rank != 0 and self.multi:
+            self.ctx.peer_close(self.ptr)

@@ -250,3 +250,30 @@ def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
         # two 256-spp estimates of the same image with DIFFERENT fp32 roundings at the hit points
         assert abs(b[2].mean() - q[2].mean()) < 0.02 * q[2].mean() + 1e-3
         assert abs(b[4] - q[4]) / q[4] < 0.01
+
+
+def test_fused_reduce_push_accum(rtb, gpu_ctx):
+    """The multi-GPU exchange step fused into the render kernel's epilogue (rt_render_opts.push_accum): three
+    'ranks' (contexts) render disjoint sample shards, each adds its accumulator into rank 0's reduce buffer; the
+    adopted image has the bits of a single render.  Both render kernels; the buffer is reusable."""
+    sc = rtb.Scene("cornell_smoke", rand_seed=1)
+    cam = sc.camera_copy(image_width=120, samples_per_pixel=36, max_depth=10)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=4)
+    whole, rays = gpu_ctx.download_accum(), gpu_ctx.stats().rays
+    others = [rtb.Context(0), rtb.Context(0)]
+    for o in others:
+        o.upload_scene(sc.desc)
+    for flags in (rtb.RT_RENDER_MEGAKERNEL, rtb.RT_RENDER_POOL):
+        ptr, handle = gpu_ctx.reduce_buffer(cam)
+        assert len(handle) == 64 and any(handle)
+        for ctx, (b, n) in zip([gpu_ctx] + others, [(0, 10), (10, 7), (17, 19)]):
+            ctx.render(cam, seed=4, sample_begin=b, sample_count=n, push_accum=ptr, flags=flags)
+        for ctx in [gpu_ctx] + others:
+            ctx.synchronize()
+        assert not np.array_equal(gpu_ctx.download_accum(), whole)  # rank 0's own accumulator holds only its shard
+        gpu_ctx.adopt_reduce_buffer()
+        assert np.array_equal(gpu_ctx.download_accum(), whole)
+        assert sum(c.stats().rays for c in [gpu_ctx] + others) == rays
+    for o in others:
+        o.close()
