@@ -759,6 +759,17 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   return RT_OK;
 }
 
+// A launch whose epilogue pushes the accumulator spins on a grid-wide arrival counter: it is launched COOPERATIVELY,
+// so the driver guarantees that all of its CTAs are resident together (or refuses the launch) whatever else runs.
+static cudaError_t launch_render(void (*kern)(RenderParams), int grid, size_t smem, cudaStream_t stream, RenderParams& P) {
+  if (P.push != nullptr) {
+    void* args[1] = {&P};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(unsigned(grid)), dim3(unsigned(kRenderThreads)), args, smem, stream);
+  }
+  kern<<<grid, kRenderThreads, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
 static void fill_camera(const rt_camera_desc* cam, const rt_camera_frame& f, CameraDev& c) {
   auto v3 = [](const double* p) { return make_float3(float(p[0]), float(p[1]), float(p[2])); };
   c.center = v3(f.center);
@@ -864,10 +875,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
     const unsigned long long zero = 0ull;  // items are handed out from 0
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, cudaFuncSetAttribute(count ? pool_kernel<true> : pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    if (count)
-      pool_kernel<true><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
-    else
-      pool_kernel<false><<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    RT_CUDA(ctx, launch_render(count ? pool_kernel<true> : pool_kernel<false>, grid, smem, ctx->stream, P));
     ctx->launches++;
   } else {
     // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared
@@ -882,7 +890,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
     // counters[0] = first item not pre-assigned to a thread
     unsigned long long first = (unsigned long long)threads;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
-    kern<<<grid, kRenderThreads, smem, ctx->stream>>>(P);
+    RT_CUDA(ctx, launch_render(kern, grid, smem, ctx->stream, P));
     ctx->launches++;
   }
   ctx->samples_total += (unsigned long long)f.image_width * f.image_height * P.sample_count;
