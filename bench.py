@@ -53,9 +53,9 @@ def parse():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--cpu-spp", type=int, default=3, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: 'fused' = every rank's render kernel adds its accumulator into rank 0's buffer from its epilogue "
-                         "(peer memory over NVLink, no collective); 'nccl' = ncclInt64 reduce after the kernel")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = behind its render kernel every rank adds its accumulator into rank 0's buffer with our own "
+                         "push kernel (peer memory over NVLink, CUDA IPC, no collective); 'nccl' = ncclInt64 reduce")
     return ap.parse_args()
 
 
@@ -250,27 +250,27 @@ def main():
         ctx.synchronize()
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    fused = None
-    if world > 1 and args.reduce == "fused":
+    peer = None
+    if world > 1 and args.reduce == "peer":
         try:
-            fused = dist.FusedReduce(ctx, cam)  # CUDA IPC + peer access; ships one 64-byte handle
+            peer = dist.PeerReduce(ctx, cam)  # CUDA IPC + peer access; ships one 64-byte handle
         except Exception as e:  # noqa: BLE001  (no peer access on this box: say so and use the collective)
-            sys.stderr.write(f"[bench] fused reduce unavailable ({e}); using NCCL\n")
-            fused = None
-        ok = torch.tensor([1 if fused is not None else 0], device=f"cuda:{local_rank}")
+            sys.stderr.write(f"[bench] peer reduce unavailable ({e}); using NCCL\n")
+            peer = None
+        ok = torch.tensor([1 if peer is not None else 0], device=f"cuda:{local_rank}")
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
         if ok.item() == 0:
-            fused = None
+            peer = None
 
     def step(seed):
         """Resident-scene step: this rank's shard + reduce; returns device ms (render + reduce)."""
         flush.fill_(1)  # L2 flush between iterations (on torch's stream; finished before the render starts)
         torch.cuda.synchronize()
-        if fused is not None:
-            # the reduce is the render kernel's epilogue: its CUDA-event time covers render + push; rank 0 adds the
-            # (wall-clock) time of adopting the reduced buffer
-            fused.render(seed)  # zero + barrier + render/push + barrier (+ adopt on rank 0)
-            return ctx.stats().last_render_ms + (fused.adopt_ms if rank == 0 else 0.0)
+        if peer is not None:
+            # the push kernel runs behind the render kernel inside the context's CUDA-event bracket: last_render_ms covers
+            # render + push; rank 0 adds the (wall-clock) time of adopting the reduced buffer
+            peer.render(seed)  # zero + barrier + render/push + barrier (+ adopt on rank 0)
+            return ctx.stats().last_render_ms + (peer.adopt_ms if rank == 0 else 0.0)
         ctx.render(cam, seed=seed, sample_begin=begin, sample_count=count, clear=True)
         ms = ctx.stats().last_render_ms  # CUDA events recorded on the context's own stream
         if world > 1:
@@ -316,8 +316,8 @@ def main():
         ta = time.time()
         ctx.upload_scene(sc.desc)  # host scene description -> device (H2D)
         tb = time.time()
-        if fused is not None:
-            fused.render(i)
+        if peer is not None:
+            peer.render(i)
             tc = time.time()
         else:
             ctx.render(cam, seed=i, sample_begin=begin, sample_count=count, clear=True)
@@ -396,7 +396,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.scene} {W}x{H} x {spp} spp, max_depth {cam.max_depth} (BASELINE config 5: 400 ground boxes, 1000-sphere cluster, "
                                    f"2 volumes, image + noise textures)", "sharding": f"sample index, {world} rank(s), exact int64 reduce to rank 0"
-                                   + ("" if world == 1 else (" fused into the render kernel's epilogue (peer red.add.u64 over NVLink)" if fused is not None else " (ncclInt64)")),
+                                   + ("" if world == 1 else (" by our push kernel behind the render (peer red.add.u64 over NVLink, no collective)" if peer is not None else " (ncclInt64)")),
                        "l2": "256 MB device write between timed steps (flush)", "seed": "Philox key = step index"},
             "mrays_per_s": mrays, "rays_per_sample": rays_per_step / total_samples, "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": total_samples / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(W * H * 3),

@@ -204,10 +204,10 @@ typedef struct rt_render_opts {
                            another context's accumulator; when non-NULL the kernel adds
                            its samples THERE (red.add.u64) instead of locally          */
   void* push_accum;     /* optional: a reduce buffer (rt_reduce_buffer of this or another
-                           rank, peer-mapped over NVLink): the render kernel accumulates
-                           locally and, once its last CTA has finished, ADDS its whole
-                           accumulator into that buffer (system-scope red.add.u64) — the
-                           multi-GPU reduce fused into the render kernel's epilogue     */
+                           rank, peer-mapped over NVLink): the render accumulates
+                           locally and a push kernel, stream-ordered right behind it,
+                           ADDS the whole accumulator into that buffer (system-scope
+                           red.add.u64) — the multi-GPU reduce without a collective    */
 } rt_render_opts;
 
 enum {
@@ -228,7 +228,7 @@ int rt_synchronize(rt_ctx* ctx);
  * as a raw device pointer, for the multi-GPU reduce (NCCL ncclInt64 sum, or peer adds). */
 int rt_accum_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
 
-/* ---- fused multi-GPU reduce (the exchange step of camera.hpp:61,65 without a collective call) ----
+/* ---- peer-memory multi-GPU reduce (the exchange step of camera.hpp:61,65 without a collective call) ----
  * Rank 0 allocates a zeroed reduce buffer (same layout as the accumulator) and exports it; the other
  * ranks (processes) open it through CUDA IPC / peer access; every rank renders its sample shard with
  * rt_render_opts.push_accum pointing at it; after a barrier rank 0 adopts the buffer as its image.   */

@@ -42,7 +42,7 @@ struct RenderParams {
   unsigned int per_chunk;  // work items per sample chunk = tiles_x * tiles_y * 32
   unsigned int n_items;
   unsigned long long* accum;     // 3 x int64 per pixel (two's complement adds)
-  unsigned long long* push;      // fused reduce: a reduce buffer (possibly another GPU's) the epilogue adds `accum` into
+  unsigned long long* push;      // peer reduce: a reduce buffer (possibly another GPU's) that push_kernel adds `accum` into
   unsigned long long n_values;   // 3 * W * H
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
@@ -72,26 +72,17 @@ __device__ __forceinline__ long long to_fixed(float v) {
   return __float2ll_rn(v * kFixScale);
 }
 
-// The multi-GPU exchange step (the per-pixel sum of camera.hpp:61 across ranks) FUSED into the render kernel: once
-// every CTA of this launch has finished accumulating (a grid-wide arrival counter; the grid is one persistent CTA
-// per SM, so spinning on it is safe), each CTA adds its slice of the local accumulator into the reduce buffer —
-// rank 0's own memory or another GPU's, peer-mapped over NVLink — with system-scope red.add.u64.  Integer adds
-// commute, so the reduced image has the same bits as a single-GPU render; no collective call, no second kernel.
-__device__ __forceinline__ void push_accumulator(const RenderParams& P) {
-  if (P.push == nullptr) return;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(P.counters + 3, 1ull);
-    while (*reinterpret_cast<volatile unsigned long long*>(P.counters + 3) < (unsigned long long)gridDim.x) __nanosleep(200);
-    __threadfence();
-  }
-  __syncthreads();
-  const unsigned long long per = (P.n_values + gridDim.x - 1) / gridDim.x;
-  const unsigned long long begin = per * blockIdx.x, end = min(begin + per, P.n_values);
-  for (unsigned long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const unsigned long long v = __ldcg(P.accum + i);  // L2: the sums were made by red.add at L2
-    if (v) atomicAdd_system(P.push + i, v);
+// The multi-GPU exchange step (the per-pixel sum of camera.hpp:61 across ranks) without a collective call: stream-
+// ordered right behind the render kernel, every rank adds its accumulator into rank 0's reduce buffer — its own memory
+// or another GPU's, peer-mapped over NVLink — with system-scope red.add.u64.  Integer adds commute, so the reduced
+// image has the bits of a single-GPU render.  15 MB per rank once per multi-second render.
+// (Doing this from the render kernel's own epilogue — grid-wide arrival counter, cooperative launch — was built and
+// worked, but the mere presence of that code cost the main loop 11 % on the headline scene through ptxas' scheduling:
+// 948 vs 1,073 Msamples/s, gpurun_out/ab_push.log.  A separate 20-microsecond kernel costs nothing.)
+__global__ void push_kernel(const unsigned long long* __restrict__ accum, unsigned long long* __restrict__ push, unsigned long long n_values) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = __ldcg(accum + i);  // L2: the sums were made by red.add at L2
+    if (v) atomicAdd_system(push + i, v);
   }
 }
 
@@ -242,7 +233,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   unsigned int rays = n_rays;
   for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
   if ((threadIdx.x & 31) == 0) atomicAdd(P.counters + 1, (unsigned long long)rays);
-  push_accumulator(P);
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++)
       if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);
@@ -759,13 +749,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   return RT_OK;
 }
 
-// A launch whose epilogue pushes the accumulator spins on a grid-wide arrival counter: it is launched COOPERATIVELY,
-// so the driver guarantees that all of its CTAs are resident together (or refuses the launch) whatever else runs.
 static cudaError_t launch_render(void (*kern)(RenderParams), int grid, size_t smem, cudaStream_t stream, RenderParams& P) {
-  if (P.push != nullptr) {
-    void* args[1] = {&P};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(unsigned(grid)), dim3(unsigned(kRenderThreads)), args, smem, stream);
-  }
   kern<<<grid, kRenderThreads, smem, stream>>>(P);
   return cudaGetLastError();
 }
@@ -841,7 +825,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   P.push = static_cast<unsigned long long*>(opts->push_accum);
   P.n_values = (unsigned long long)f.image_width * f.image_height * 3ull;
   if (P.push && opts->peer_accum) return fail(ctx, RT_ERR_INVALID, "peer_accum and push_accum are mutually exclusive");
-  if (P.push) RT_CUDA(ctx, cudaMemsetAsync(ctx->counters + 3, 0, sizeof(unsigned long long), ctx->stream));  // the epilogue's arrival counter
+
   P.counters = ctx->counters;
   P.smem_nodes = ctx->smem_nodes;
   size_t smem = size_t(P.smem_nodes) * 64;
@@ -895,6 +879,11 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   }
   ctx->samples_total += (unsigned long long)f.image_width * f.image_height * P.sample_count;
   RT_CUDA(ctx, cudaGetLastError());
+  if (P.push) {  // the exchange step, stream-ordered behind the render (inside the timed region)
+    push_kernel<<<2 * grid, 512, 0, ctx->stream>>>(ctx->accum, P.push, P.n_values);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+  }
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
   return RT_OK;

@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) pool_kernel(const __grid_co
     const unsigned int rays = reinterpret_cast<unsigned int*>(pool + kPoolCtlOff)[QC_RAYS];
     if (rays) atomicAdd(P.counters + 1, (unsigned long long)rays);
   }
-  push_accumulator(P);
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++)
       if (cn[i]) atomicAdd(P.counters + 4 + i, (unsigned long long)cn[i]);

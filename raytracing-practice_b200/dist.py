@@ -65,10 +65,11 @@ def render_sharded(ctx, cam, seed=0):
         torch.cuda.synchronize()
 
 
-class FusedReduce:
-    """The exchange step without a collective call: rank 0 owns a reduce buffer, every rank's render kernel adds its
-    accumulator into it from its epilogue (rt_render_opts.push_accum: system-scope red.add.u64 over NVLink peer memory
-    for the other ranks).  torch.distributed only ships the 64-byte IPC handle once and provides the barriers."""
+class PeerReduce:
+    """The exchange step without a collective call: rank 0 owns a reduce buffer; stream-ordered behind its render
+    kernel, every rank's push kernel adds the rank's accumulator into it (rt_render_opts.push_accum: system-scope
+    red.add.u64, over NVLink peer memory for the other ranks).  torch.distributed only ships the 64-byte IPC handle
+    once and provides the barriers."""
 
     def __init__(self, ctx, cam):
         import torch
@@ -89,7 +90,7 @@ class FusedReduce:
                 self.ptr = ctx.peer_open(bytes(t.cpu().tolist()))
 
     def render(self, seed=0):
-        """One frame: zero the buffer (rank 0), barrier, every rank renders its shard and pushes, barrier, rank 0 adopts."""
+        """One frame: zero the buffer (rank 0), barrier, every rank renders its shard and pushes it, barrier, rank 0 adopts."""
         import torch
         import torch.distributed as dist
 

@@ -252,10 +252,10 @@ def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
         assert abs(b[4] - q[4]) / q[4] < 0.01
 
 
-def test_fused_reduce_push_accum(rtb, gpu_ctx):
-    """The multi-GPU exchange step fused into the render kernel's epilogue (rt_render_opts.push_accum): three
-    'ranks' (contexts) render disjoint sample shards, each adds its accumulator into rank 0's reduce buffer; the
-    adopted image has the bits of a single render.  Both render kernels; the buffer is reusable."""
+def test_peer_reduce_push_accum(rtb, gpu_ctx):
+    """The multi-GPU exchange step without a collective (rt_render_opts.push_accum): three 'ranks' (contexts) render
+    disjoint sample shards, behind each render a push kernel adds the rank's accumulator into rank 0's reduce buffer;
+    the adopted image has the bits of a single render.  Both render kernels; the buffer is reusable."""
     sc = rtb.Scene("cornell_smoke", rand_seed=1)
     cam = sc.camera_copy(image_width=120, samples_per_pixel=36, max_depth=10)
     gpu_ctx.upload_scene(sc.desc)
