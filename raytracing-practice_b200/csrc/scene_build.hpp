@@ -394,9 +394,9 @@ struct SahBuilder {
   std::vector<Item>& items;
   std::vector<TmpNode> nodes;
   std::vector<Item> ordered;
-  // SAH constants in units of one node visit (two slab tests).  A leaf primitive costs more than its flop count
-  // says because leaf steps run at low SIMD efficiency; values fitted on the GPU (profiles/r08_sah_constants.md).
-  double prim_scale = 0.5;
+  // SAH constants in units of one node visit (two slab tests), fitted on the GPU (profiles/r08_sah_constants.md):
+  // 0.5 while a node step cost ~75 instructions, 1.0 since the traversal diet brought it down to 52.
+  double prim_scale = 1.0;
   int max_leaf = kMaxLeaf;
   explicit SahBuilder(std::vector<Item>& it) : items(it) {
     if (const char* e = std::getenv("RT_B200_SAH_PRIM")) prim_scale = std::max(0.01, std::atof(e));
