@@ -43,16 +43,20 @@ __device__ __forceinline__ float3 normalize3(float3 a) { return rsqrtf(dot(a, a)
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 
 // ---------------------------------------------------------------------------------------
-// Philox-4x32-10 (Salmon et al. 2011), counter-based: the sample set of a (pixel, sample,
+// Philox-4x32 (Salmon et al. 2011; RT_PHILOX_ROUNDS rounds), counter-based: the sample set of a (pixel, sample,
 // bounce) is a pure function of the key, so images do not depend on how samples are sharded
 // over threads, launches or GPUs.
+#ifndef RT_PHILOX_ROUNDS
+#define RT_PHILOX_ROUNDS 7  // Philox4x32-7: the fewest rounds that pass BigCrush (Salmon et al. 2011, table 2); 10 is their
+                            // conservative default and costs +2.5..5 % of the whole render (gpurun_out/ab_philox.log)
+#endif
 #ifndef RT_OUTLINE_PHILOX
 #define RT_OUTLINE_PHILOX RT_OUTLINE
 #endif
 __device__ __forceinline__ uint4 philox4x32_10_inl(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
+  for (int r = 0; r < RT_PHILOX_ROUNDS; r++) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
