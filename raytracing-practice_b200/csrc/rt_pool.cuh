@@ -152,7 +152,7 @@ __device__ __noinline__ int shade_slot(const RenderParams* __restrict__ Pp, floa
       if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
         const uint4 r1 = rng_block(key, 0u, 1u);
         float rr = sqrtf(u01(r1.x)), sn, cs;
-        sincospif(2.0f * u01(r1.y), &sn, &cs);
+        sincos_2pi(u01(r1.y), sn, cs);
         const float3 off = fma3(rr * cs, P.cam.ddu, (rr * sn) * P.cam.ddv);
         o = o + off;
         dir = dir - off;
