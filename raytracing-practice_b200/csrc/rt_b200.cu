@@ -789,9 +789,38 @@ static int ensure_accum(rt_ctx* ctx, int W, int H, bool clear) {
   return RT_OK;
 }
 
+static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts, bool first_piece, bool last_piece);
+
+// One kernel launch addresses < 2^32 work items (pixel tile x chunk of 32 samples).  A request beyond that — e.g.
+// 4096 x 4096 at 10,000 spp — is rendered as several stream-ordered launches over consecutive sample ranges; the
+// fixed-point sums make the split invisible in the image.
 int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts) {
   if (!ctx) return RT_ERR_INVALID;
   if (!cam || !opts) return fail(ctx, RT_ERR_INVALID, "null camera / options");
+  if (cam->image_width <= 0 || cam->samples_per_pixel <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
+  rt_camera_frame f;
+  rt_camera_initialize(cam, &f);
+  const long long count = opts->sample_count > 0 ? opts->sample_count : (long long)cam->samples_per_pixel - opts->sample_begin;
+  const unsigned long long per_chunk = (unsigned long long)((f.image_width + 7) / 8) * (unsigned long long)((f.image_height + 3) / 4) * 32ull;
+  unsigned long long max_chunks = (0xFFFFFFFFull - (unsigned long long)ctx->sm_count * kRenderThreads - 1ull) / per_chunk;
+  if (const char* e = std::getenv("RT_B200_MAX_CHUNKS")) max_chunks = std::min<unsigned long long>(max_chunks, std::max(1, std::atoi(e)));  // test hook
+  if (max_chunks == 0) return fail(ctx, RT_ERR_INVALID, "image too large (more than 2^32 pixels per launch)");
+  const long long cap = (long long)std::min<unsigned long long>(max_chunks * 32ull, 1ull << 30);
+  if (count <= cap) return render_range(ctx, cam, opts, true, true);
+  rt_render_opts piece = *opts;
+  for (long long done = 0; done < count; done += cap) {
+    piece.sample_begin = int32_t(opts->sample_begin + done);
+    piece.sample_count = int32_t(std::min(cap, count - done));
+    piece.clear = done == 0 ? opts->clear : 0;
+    const bool last = done + cap >= count;
+    piece.push_accum = last ? opts->push_accum : nullptr;
+    int rc = render_range(ctx, cam, &piece, done == 0, last);
+    if (rc != RT_OK) return rc;
+  }
+  return RT_OK;
+}
+
+static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts, bool first_piece, bool last_piece) {
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_render before rt_upload_scene");
   if (cam->image_width <= 0 || cam->samples_per_pixel <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -835,7 +864,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   if (const char* e = std::getenv("RT_B200_KERNEL")) pool = std::string(e) == "pool" ? true : (std::string(e) == "mega" ? false : pool);
   if (opts->flags & RT_RENDER_MEGAKERNEL) pool = false;
   if (opts->flags & RT_RENDER_POOL) pool = true;
-  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (first_piece) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.cam.max_depth <= 0) {
     // ray_color returns black at once (camera.hpp:183-186): nothing to trace, the sums stay as they are
   } else if (pool) {
@@ -884,8 +913,10 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
   }
-  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->timed = true;
+  if (last_piece) {
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->timed = true;
+  }
   return RT_OK;
 }
 

@@ -277,3 +277,24 @@ def test_peer_reduce_push_accum(rtb, gpu_ctx):
         assert sum(c.stats().rays for c in [gpu_ctx] + others) == rays
     for o in others:
         o.close()
+
+
+def test_oversized_render_is_split_into_launches(rtb, gpu_ctx, monkeypatch):
+    """A request with more than 2^32 work items is rendered as several launches over consecutive sample ranges
+    (rt_render); RT_B200_MAX_CHUNKS lowers the per-launch limit so the split can be exercised at test size.  Same
+    accumulator bits, ray and sample counts, and the peer push happens once, after the last piece."""
+    sc = rtb.Scene("bouncing_spheres", rand_seed=1)
+    cam = sc.camera_copy(image_width=120, samples_per_pixel=150)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=6)
+    whole, st = gpu_ctx.download_accum(), gpu_ctx.stats()
+    launches0 = st.kernel_launches
+    monkeypatch.setenv("RT_B200_MAX_CHUNKS", "2")  # 64 samples per launch -> 3 launches
+    gpu_ctx.render(cam, seed=6)
+    st2 = gpu_ctx.stats()
+    assert np.array_equal(gpu_ctx.download_accum(), whole) and st2.rays == st.rays and st2.samples == st.samples
+    assert st2.kernel_launches - launches0 == 3
+    ptr, _ = gpu_ctx.reduce_buffer(cam)
+    gpu_ctx.render(cam, seed=6, push_accum=ptr, flags=rtb.RT_RENDER_POOL)
+    gpu_ctx.adopt_reduce_buffer()
+    assert np.array_equal(gpu_ctx.download_accum(), whole)
