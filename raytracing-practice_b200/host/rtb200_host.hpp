@@ -975,12 +975,13 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
       if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_download", rc);
       for (size_t i = 0; i < total.size(); i++) total[i] += part[i];
     }
-    const double scale = (1.0f / samples_per_pixel) / 4294967296.0;
-    const float hi = 0.999f;
+    // write_color (common/color.hpp:26-58) in double, operation for operation what the device's finalize kernel does
+    const double scale = double(1.0f / float(samples_per_pixel));  // pixel_samples_scale, camera.hpp:83
+    const double hi = double(0.999f);
     for (size_t i = 0; i < total.size(); i++) {
-      float lin = float(double(total[i]) * scale);
-      float g = lin > 0.0f ? std::sqrt(lin) : 0.0f;
-      g = g < 0.0f ? 0.0f : (g > hi ? hi : g);
+      const double lin = double(total[i]) * (1.0 / 4294967296.0) * scale;
+      double g = lin > 0.0 ? std::sqrt(lin) : 0.0;
+      g = g < 0.0 ? 0.0 : (g > hi ? hi : g);
       rgb[i] = uint8_t(int(256 * g));
     }
   }
