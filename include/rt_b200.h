@@ -237,6 +237,9 @@ typedef struct rt_ipc_handle {
 } rt_ipc_handle;
 int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_ipc_handle* handle /* may be NULL */);
 int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr);
+/* Same process, several devices (the C++ host's RT_B200_DEVICES path): lets ctx's device address `owner`'s
+ * memory directly (cudaDeviceEnablePeerAccess); a no-op when both contexts sit on the same device.      */
+int rt_peer_enable(rt_ctx* ctx, rt_ctx* owner);
 int rt_peer_close(rt_ctx* ctx, void* dev_ptr);
 /* Copies the reduce buffer over the context's accumulator (rt_download / rt_accum_device_ptr then read the
  * reduced image).  The buffer and its handle stay valid: rt_reduce_buffer with the same camera re-zeroes it. */

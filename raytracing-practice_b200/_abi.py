@@ -171,6 +171,7 @@ C_ABI_SYMBOLS = [
     "rt_accum_device_ptr",
     "rt_reduce_buffer",
     "rt_peer_open",
+    "rt_peer_enable",
     "rt_peer_close",
     "rt_adopt_reduce_buffer",
     "rt_download",

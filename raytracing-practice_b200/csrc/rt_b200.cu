@@ -973,6 +973,22 @@ int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr) {
   return RT_OK;
 }
 
+int rt_peer_enable(rt_ctx* ctx, rt_ctx* owner) {
+  if (!ctx || !owner) return RT_ERR_INVALID;
+  if (ctx->device == owner->device) return RT_OK;
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  int can = 0;
+  RT_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, owner->device));
+  if (!can) return fail(ctx, RT_ERR_UNSUPPORTED, "no peer access between devices " + std::to_string(ctx->device) + " and " + std::to_string(owner->device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    e = cudaSuccess;
+  }
+  RT_CUDA(ctx, e);
+  return RT_OK;
+}
+
 int rt_peer_close(rt_ctx* ctx, void* dev_ptr) {
   if (!ctx) return RT_ERR_INVALID;
   RT_CUDA(ctx, cudaSetDevice(ctx->device));

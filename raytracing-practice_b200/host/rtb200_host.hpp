@@ -952,6 +952,18 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
     rc = rt_upload_scene(ctx[size_t(r)], &sd);
     if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rc);
   }
+  // Several devices: the exchange step (the per-pixel sum of camera.hpp:61) is done on the devices — every context
+  // adds its accumulator into the first one's reduce buffer over peer memory (rt_render_opts.push_accum), no host sum.
+  // Devices without peer access to the first one fall back to the exact integer sum on the host.
+  void* reduce = nullptr;
+  bool on_device = R > 1;
+  if (R > 1) {
+    for (int r = 1; r < R && on_device; r++) on_device = rt_peer_enable(ctx[size_t(r)], ctx[0]) == RT_OK;
+    if (on_device) {
+      int rc = rt_reduce_buffer(ctx[0], &cam, &reduce, nullptr);
+      if (rc != RT_OK) rtb200::die(ctx[0], "rt_reduce_buffer", rc);
+    }
+  }
   for (int r = 0; r < R; r++) {  // asynchronous: all devices render concurrently
     rt_render_opts o;
     std::memset(&o, 0, sizeof o);
@@ -959,12 +971,21 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
     o.sample_begin = int32_t((int64_t(samples_per_pixel) * r) / R);
     o.sample_count = int32_t((int64_t(samples_per_pixel) * (r + 1)) / R) - o.sample_begin;
     o.clear = 1;
+    o.push_accum = on_device ? reduce : nullptr;
     int rc = rt_render(ctx[size_t(r)], &cam, &o);
     if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_render", rc);
   }
   const size_t npix = size_t(frame.image_width) * frame.image_height;
   std::vector<uint8_t> rgb(npix * 3);
-  if (R == 1) {
+  if (R == 1 || on_device) {
+    if (on_device) {
+      for (int r = 0; r < R; r++) {
+        int rc = rt_synchronize(ctx[size_t(r)]);
+        if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_synchronize", rc);
+      }
+      int rc = rt_adopt_reduce_buffer(ctx[0]);
+      if (rc != RT_OK) rtb200::die(ctx[0], "rt_adopt_reduce_buffer", rc);
+    }
     int rc = rt_download(ctx[0], RT_BUF_RGB8, samples_per_pixel, rgb.data(), rgb.size());
     if (rc != RT_OK) rtb200::die(ctx[0], "rt_download", rc);
   } else {
