@@ -703,6 +703,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   }
   const HostScene& h = ctx->host;
   if (h.bvh_depth > kStackDepth) return fail(ctx, RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+  if (h.leaf_refs.size() >= (size_t(1) << 27)) return fail(ctx, RT_ERR_UNSUPPORTED, "too many leaf references for the 32-bit leaf code");
   DeviceScene& s = ctx->sc;
   int rc;
 #define UP(field, vec) \
