@@ -506,6 +506,20 @@ struct rt_ctx {
     }                                                                                               \
   } while (0)
 
+// RT_B200_DEBUG=1: entry points report a CUDA error that is already pending when they start / still pending when they
+// return, on stderr.  A non-sticky error left by an unrelated earlier call (anywhere in the process) would otherwise be
+// blamed on the next cudaGetLastError() after one of OUR launches; every entry point clears it first.
+static void debug_error(const char* where, bool clear) {
+  cudaError_t e = clear ? cudaGetLastError() : cudaPeekAtLastError();
+  if (e != cudaSuccess && std::getenv("RT_B200_DEBUG"))
+    std::fprintf(stderr, "[rt_b200] %s: CUDA error '%s' %s\n", where, cudaGetErrorString(e), clear ? "was pending (cleared)" : "left pending");
+}
+struct DebugScope {
+  const char* name;
+  explicit DebugScope(const char* n) : name(n) { debug_error(n, true); }
+  ~DebugScope() { debug_error(name, false); }
+};
+
 static int fail(rt_ctx* ctx, int code, const std::string& msg) {
   ctx->error = msg;
   return code;
@@ -524,7 +538,11 @@ static int upload(rt_ctx* ctx, const std::vector<T>& v, const T** out) {
 }
 
 static void free_scene(rt_ctx* ctx) {
-  for (void* p : ctx->scene_allocs) cudaFree(p);
+  for (size_t i = 0; i < ctx->scene_allocs.size(); i++) {
+    cudaError_t e = cudaFree(ctx->scene_allocs[i]);
+    if (e != cudaSuccess && std::getenv("RT_B200_DEBUG"))
+      std::fprintf(stderr, "[rt_b200] free_scene: cudaFree(alloc #%zu = %p) -> %s\n", i, ctx->scene_allocs[i], cudaGetErrorString(e));
+  }
   ctx->scene_allocs.clear();
   ctx->has_scene = false;
 }
@@ -670,6 +688,7 @@ int rt_init(int device, rt_ctx** out) {
 
 void rt_shutdown(rt_ctx* ctx) {
   if (!ctx) return;
+  DebugScope dbg("rt_shutdown");
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_scene(ctx);
@@ -692,6 +711,7 @@ const char* rt_last_error(rt_ctx* ctx) {
 
 int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_upload_scene");
   if (!scene) return fail(ctx, RT_ERR_INVALID, "null scene");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -822,6 +842,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
 }
 
 static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts, bool first_piece, bool last_piece) {
+  DebugScope dbg("rt_render");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_render before rt_upload_scene");
   if (cam->image_width <= 0 || cam->samples_per_pixel <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -923,6 +944,7 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
 
 int rt_synchronize(rt_ctx* ctx) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_synchronize");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return RT_OK;
@@ -939,6 +961,7 @@ int rt_accum_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes) {
 // ---- fused multi-GPU reduce: a reduce buffer other ranks' render kernels add their accumulators into ----------
 int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_ipc_handle* handle) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_reduce_buffer");
   if (!cam || !dev_ptr || cam->image_width <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera / null output");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   rt_camera_frame f;
@@ -947,7 +970,6 @@ int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_
   if (values != ctx->reduce_values) {
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->reduce_buf);
-  cudaFree(ctx->scratch);
     ctx->reduce_buf = nullptr, ctx->reduce_values = 0;
     RT_CUDA(ctx, cudaMalloc(&ctx->reduce_buf, values * 8));
     ctx->reduce_values = values;
@@ -966,6 +988,7 @@ int rt_reduce_buffer(rt_ctx* ctx, const rt_camera_desc* cam, void** dev_ptr, rt_
 
 int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_peer_open");
   if (!handle || !dev_ptr) return fail(ctx, RT_ERR_INVALID, "null handle / output");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaIpcMemHandle_t h;
@@ -976,6 +999,7 @@ int rt_peer_open(rt_ctx* ctx, const rt_ipc_handle* handle, void** dev_ptr) {
 
 int rt_peer_enable(rt_ctx* ctx, rt_ctx* owner) {
   if (!ctx || !owner) return RT_ERR_INVALID;
+  DebugScope dbg("rt_peer_enable");
   if (ctx->device == owner->device) return RT_OK;
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   int can = 0;
@@ -992,6 +1016,7 @@ int rt_peer_enable(rt_ctx* ctx, rt_ctx* owner) {
 
 int rt_peer_close(rt_ctx* ctx, void* dev_ptr) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_peer_close");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   RT_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
@@ -1000,6 +1025,7 @@ int rt_peer_close(rt_ctx* ctx, void* dev_ptr) {
 
 int rt_adopt_reduce_buffer(rt_ctx* ctx) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_adopt_reduce_buffer");
   if (!ctx->reduce_buf) return fail(ctx, RT_ERR_INVALID, "no reduce buffer (call rt_reduce_buffer first)");
   if (ctx->reduce_values != ctx->accum_values || !ctx->accum) return fail(ctx, RT_ERR_INVALID, "reduce buffer and accumulator differ in size");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1011,6 +1037,7 @@ int rt_adopt_reduce_buffer(rt_ctx* ctx) {
 
 int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t bytes) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_download");
   if (!dst) return fail(ctx, RT_ERR_INVALID, "null destination");
   if (!ctx->accum) return fail(ctx, RT_ERR_INVALID, "nothing rendered yet");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1077,6 +1104,7 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
 int rt_trace_rays(rt_ctx* ctx, int64_t n, const double* origin, const double* direction, const double* time, double tmin, double tmax, int32_t flags,
                   int32_t* prim_id, double* t, double* normal, uint8_t* front_face) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_trace_rays");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_trace_rays before rt_upload_scene");
   if (n < 0 || (n > 0 && (!origin || !direction))) return fail(ctx, RT_ERR_INVALID, "bad ray arrays");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1090,6 +1118,7 @@ int rt_trace_rays(rt_ctx* ctx, int64_t n, const double* origin, const double* di
 
 int rt_primary_visibility(rt_ctx* ctx, const rt_camera_desc* cam, int32_t flags, int32_t* prim_id, double* t, double* normal) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_primary_visibility");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_primary_visibility before rt_upload_scene");
   if (!cam || cam->image_width <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1110,6 +1139,7 @@ int rt_primary_visibility(rt_ctx* ctx, const rt_camera_desc* cam, int32_t flags,
 int rt_medium_spans(rt_ctx* ctx, int32_t medium_index, int64_t n, const double* origin, const double* direction, const double* time, double* t1,
                     double* t2) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_medium_spans");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_medium_spans before rt_upload_scene");
   if (medium_index < 0 || medium_index >= ctx->sc.n_media) return fail(ctx, RT_ERR_INVALID, "medium index out of range");
   if (n < 0 || !origin || !direction || !t1 || !t2) return fail(ctx, RT_ERR_INVALID, "bad arrays");
@@ -1134,6 +1164,7 @@ int rt_medium_spans(rt_ctx* ctx, int32_t medium_index, int64_t n, const double* 
 
 int rt_eval_texture(rt_ctx* ctx, int32_t texture, int64_t n, const double* uvp, float* rgb) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_eval_texture");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_eval_texture before rt_upload_scene");
   if (texture < 0 || texture >= ctx->sc.n_textures) return fail(ctx, RT_ERR_INVALID, "texture index out of range");
   if (n < 0 || !uvp || !rgb) return fail(ctx, RT_ERR_INVALID, "bad arrays");
@@ -1155,6 +1186,7 @@ int rt_eval_texture(rt_ctx* ctx, int32_t texture, int64_t n, const double* uvp, 
 int rt_eval_scatter(rt_ctx* ctx, int32_t material, int64_t n, uint64_t seed, const double* dir_in, const double* normal, const uint8_t* front_face,
                     float* dir_out, float* attenuation, uint8_t* scattered) {
   if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_eval_scatter");
   if (!ctx->has_scene) return fail(ctx, RT_ERR_NO_SCENE, "rt_eval_scatter before rt_upload_scene");
   if (material < 0 || material >= ctx->sc.n_materials) return fail(ctx, RT_ERR_INVALID, "material index out of range");
   if (n < 0 || !dir_in || !normal || !front_face || !dir_out || !attenuation || !scattered) return fail(ctx, RT_ERR_INVALID, "bad arrays");
