@@ -126,3 +126,49 @@ def test_reference_main_cpp_compiles_unchanged_against_the_host_api(rtb, tmp_pat
     if not torch.cuda.is_available():
         out = subprocess.run([exe, str(tmp_path / "image.ppm")], capture_output=True, text=True, cwd=str(tmp_path))
         assert out.returncode != 0 and "rt_init" in out.stderr
+
+
+def test_box_lists_are_recognised_only_when_they_are_boxes(rtb, built):
+    """The flattener turns a hittable_list into ONE slab-test primitive only if it is what box() builds
+    (quad.hpp:129-159): six axis-aligned rectangles of one material tiling the surface of [lo, hi] — corners that are
+    min + (max - min) may differ from max in the last bit.  Anything else stays six quads."""
+    import numpy as np
+    import scene_util as su
+
+    lib = C.CDLL(rtb.CUDA_LIB_PATH)
+    lib.rt_debug_build_stats.argtypes = [C.POINTER(rtb.rt_scene_desc), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+
+    def boxes_of(build):
+        s = su.SceneDesc()
+        mat = s.lambertian(s.solid(0.5, 0.5, 0.5))
+        root = build(s, mat)
+        cnt = (C.c_int32 * 16)()
+        assert lib.rt_debug_build_stats(s.finish(root), cnt, None) == 0
+        return cnt[8], cnt[2]
+
+    rng = np.random.default_rng(0)
+    for _ in range(50):  # awkward doubles: lo + (hi - lo) != hi for many of these
+        a, b = tuple(rng.uniform(-3, 0, 3) * np.pi), tuple(rng.uniform(0.1, 7, 3) / 3.0)
+        assert boxes_of(lambda s, m: s.box(a, b, m)) == (1, 6)
+    # instanced: translate(rotate_y(box)) is still one primitive
+    assert boxes_of(lambda s, m: s.translate(s.rotate_y(s.box((0, 0, 0), (1, 2, 3), m), 33.0), (4, 5, 6))) == (1, 6)
+    # two boxes in one list of 12 quads are not "a box"
+    assert boxes_of(lambda s, m: s.list(s.children[s.h[s.box((0, 0, 0), (1, 1, 1), m)].child0:][:6] + s.children[s.h[s.box((2, 0, 0), (3, 1, 1), m)].child0:][:6]))[0] == 0
+
+    def open_box(s, m):  # five faces + a lid that does not span the face
+        k = s.box((0, 0, 0), (1, 1, 1), m)
+        kids = s.children[s.h[k].child0:s.h[k].child0 + 6]
+        kids[4] = s.quad((0, 1, 1), (0.5, 0, 0), (0, 0, -1), m)
+        return s.list(kids)
+
+    assert boxes_of(open_box)[0] == 0
+
+    def two_materials(s, m):
+        k = s.box((0, 0, 0), (1, 1, 1), m)
+        kids = s.children[s.h[k].child0:s.h[k].child0 + 6]
+        s.h[kids[2]].material = s.lambertian(s.solid(1, 0, 0))
+        return s.list(kids)
+
+    assert boxes_of(two_materials)[0] == 0
+    # a sheared "box" (parallelogram faces) is not axis-aligned
+    assert boxes_of(lambda s, m: s.list([s.quad((0, 0, 0), (1, 0.2, 0), (0, 1, 0), m) for _ in range(6)]))[0] == 0
