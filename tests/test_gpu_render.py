@@ -298,3 +298,44 @@ def test_oversized_render_is_split_into_launches(rtb, gpu_ctx, monkeypatch):
     gpu_ctx.render(cam, seed=6, push_accum=ptr, flags=rtb.RT_RENDER_POOL)
     gpu_ctx.adopt_reduce_buffer()
     assert np.array_equal(gpu_ctx.download_accum(), whole)
+
+
+@pytest.mark.parametrize("width,aspect,spp", [(1, 1.0, 1), (7, 7 / 5, 3), (33, 16 / 9, 1), (257, 4.0, 2)])
+def test_ragged_image_sizes_and_tiny_jobs(rtb, gpu_ctx, width, aspect, spp):
+    """Images that are not a multiple of the 8x4 work tile, a single pixel, a single sample: every (pixel, sample)
+    is rendered exactly once by either kernel (sample accounting, bit-identical accumulators), rows x columns follow
+    camera::initialize (int(W / aspect) clamped to >= 1, camera.hpp:79-80)."""
+    sc = rtb.Scene("cornell_box", rand_seed=1)
+    cam = sc.camera_copy(image_width=width, samples_per_pixel=spp, max_depth=6)
+    cam.aspect_ratio = aspect
+    gpu_ctx.upload_scene(sc.desc)
+    h = max(1, int(width / aspect))
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_MEGAKERNEL)
+    a, st = gpu_ctx.download_accum(), gpu_ctx.stats()
+    assert a.shape == (h, width, 3) and st.samples == width * h * spp and st.rays >= st.samples
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_POOL)
+    assert np.array_equal(gpu_ctx.download_accum(), a) and gpu_ctx.stats().rays == st.rays
+    # one sample at a time, accumulated: same bits
+    for s in range(spp):
+        gpu_ctx.render(cam, seed=2, sample_begin=s, sample_count=1, clear=(s == 0))
+    assert np.array_equal(gpu_ctx.download_accum(), a)
+    assert gpu_ctx.download_rgb8(spp).shape == (h, width, 3)
+
+
+def test_render_option_errors(rtb, gpu_ctx):
+    sc = rtb.Scene("quads", rand_seed=1)
+    cam = sc.camera_copy(image_width=32, samples_per_pixel=4)
+    gpu_ctx.upload_scene(sc.desc)
+    ptr, _ = gpu_ctx.reduce_buffer(cam)
+    with pytest.raises(rtb.RtError, match="mutually exclusive"):
+        gpu_ctx.render(cam, peer_accum=ptr, push_accum=ptr)
+    with pytest.raises(rtb.RtError, match="empty sample range"):
+        gpu_ctx.render(cam, sample_begin=4)
+    with pytest.raises(rtb.RtError, match="empty sample range"):
+        gpu_ctx.render(cam, sample_begin=-1, sample_count=2)
+    big = sc.camera_copy(image_width=64, samples_per_pixel=4)
+    gpu_ctx.render(big)
+    with pytest.raises(rtb.RtError, match="differ in size"):
+        gpu_ctx.adopt_reduce_buffer()  # the reduce buffer was made for the 32-wide camera
+    gpu_ctx.render(cam, seed=1)  # still usable afterwards
+    assert gpu_ctx.stats().samples == 32 * 32 * 4
