@@ -257,6 +257,12 @@ typedef enum rt_buffer_kind {
 int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t samples_per_pixel, void* dst,
                 size_t bytes);
 
+/* The inverse of rt_download(RT_BUF_ACCUM_I64): replaces the context's accumulator with image_width x image_height x 3
+ * int64 sums from host memory (bytes must be exactly that), e.g. the sums a checkpoint saved.  A following
+ * rt_render with clear == 0 and the next sample_begin continues the render; because the sums are integers the
+ * finished image has the bits of an uninterrupted one (camera.hpp:55-61 is a plain sum over samples).            */
+int rt_upload_accum(rt_ctx* ctx, const rt_camera_desc* cam, const void* src, size_t bytes);
+
 typedef struct rt_stats {
   uint64_t rays;        /* closest-hit queries issued by the integrator since the last
                            clear (= world.hit calls at camera.hpp:192)                 */

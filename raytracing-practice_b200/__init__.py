@@ -58,6 +58,7 @@ def cuda_lib():
         lib.rt_peer_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.rt_adopt_reduce_buffer.argtypes = [C.c_void_p]
         lib.rt_download.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_size_t]
+        lib.rt_upload_accum.argtypes = [C.c_void_p, C.POINTER(_abi.rt_camera_desc), C.c_void_p, C.c_size_t]
         lib.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.rt_stats)]
         lib.rt_camera_initialize.argtypes = [C.POINTER(_abi.rt_camera_desc), C.POINTER(_abi.rt_camera_frame)]
         dp, ip, bp, fp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
@@ -224,6 +225,11 @@ class Context:
     def download_accum(self):
         s = self.stats()
         return self._download(RT_BUF_ACCUM_I64, 1, np.empty((s.image_height, s.image_width, 3), np.int64))
+
+    def upload_accum(self, cam, sums):
+        """Replace the accumulator with saved int64 sums (H x W x 3): the inverse of download_accum."""
+        a = np.ascontiguousarray(sums, dtype=np.int64)
+        self._check(self._lib.rt_upload_accum(self._h, C.byref(cam), a.ctypes.data_as(C.c_void_p), a.nbytes), "rt_upload_accum")
 
     def download_radiance(self, spp):
         s = self.stats()

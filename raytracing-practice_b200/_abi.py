@@ -175,6 +175,7 @@ C_ABI_SYMBOLS = [
     "rt_peer_close",
     "rt_adopt_reduce_buffer",
     "rt_download",
+    "rt_upload_accum",
     "rt_get_stats",
     "rt_trace_rays",
     "rt_primary_visibility",

@@ -1035,6 +1035,22 @@ int rt_adopt_reduce_buffer(rt_ctx* ctx) {
   return RT_OK;
 }
 
+int rt_upload_accum(rt_ctx* ctx, const rt_camera_desc* cam, const void* src, size_t bytes) {
+  if (!ctx) return RT_ERR_INVALID;
+  DebugScope dbg("rt_upload_accum");
+  if (!cam || !src || cam->image_width <= 0 || !(cam->aspect_ratio > 0)) return fail(ctx, RT_ERR_INVALID, "bad camera / null source");
+  RT_CUDA(ctx, cudaSetDevice(ctx->device));
+  rt_camera_frame f;
+  rt_camera_initialize(cam, &f);
+  const size_t values = size_t(f.image_width) * f.image_height * 3;
+  if (bytes != values * 8) return fail(ctx, RT_ERR_INVALID, "source is not image_width x image_height x 3 int64 sums");
+  int rc = ensure_accum(ctx, f.image_width, f.image_height, true);  // also resets the ray / sample counters
+  if (rc != RT_OK) return rc;
+  RT_CUDA(ctx, cudaMemcpyAsync(ctx->accum, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // src may be pageable and may be freed by the caller right away
+  return RT_OK;
+}
+
 int rt_download(rt_ctx* ctx, rt_buffer_kind kind, int32_t spp, void* dst, size_t bytes) {
   if (!ctx) return RT_ERR_INVALID;
   DebugScope dbg("rt_download");

@@ -918,8 +918,88 @@ inline void write_ppm_p3(std::ostream& out, int w, int h, const uint8_t* rgb) {
   }
   out.write(buf.data(), std::streamsize(buf.size()));
 }
+// Binary side output: the same bytes the P3 text spells out, as a P6 file.
+inline bool write_ppm_p6(const char* path, int w, int h, const uint8_t* rgb) {
+  std::FILE* f = std::fopen(path, "wb");
+  if (!f) return false;
+  std::fprintf(f, "P6\n%d %d\n255\n", w, h);
+  const size_t n = size_t(w) * h * 3;
+  const bool ok = std::fwrite(rgb, 1, n, f) == n;
+  return (std::fclose(f) == 0) && ok;
+}
+
+// ---- checkpointed progressive rendering ---------------------------------------------
+// camera::render's sample loop (camera.hpp:55-61) is a plain sum, the device keeps it as exact int64 fixed-point
+// sums, and sample s of pixel p draws from Philox counter (p, s, bounce): a render can therefore stop after any
+// number of samples and continue later — in another process, on another number of GPUs — and the finished image
+// has the bits of an uninterrupted one.  The file holds a header and the W x H x 3 int64 sums.
+struct checkpoint_header {
+  char magic[8];  // "RTB2CKPT"
+  uint32_t version, width, height, spp_total, spp_done, max_depth;
+  uint64_t seed, scene_hash;  // FNV-1a over the camera and the flattened scene description
+};
+inline uint64_t fnv1a(uint64_t h, const void* data, size_t bytes) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < bytes; i++) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+inline uint64_t scene_hash(const rt_scene_desc& d, const rt_camera_desc& cam) {
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, &cam, sizeof cam);
+  h = fnv1a(h, &d.root, sizeof d.root);
+  h = fnv1a(h, d.hittables, size_t(d.n_hittables) * sizeof(rt_hittable));
+  h = fnv1a(h, d.child_index, size_t(d.n_child_index) * sizeof(int32_t));
+  h = fnv1a(h, d.materials, size_t(d.n_materials) * sizeof(rt_material));
+  h = fnv1a(h, d.textures, size_t(d.n_textures) * sizeof(rt_texture));
+  h = fnv1a(h, d.perlins, size_t(d.n_perlins) * sizeof(rt_perlin));
+  for (int i = 0; i < d.n_images; i++) {
+    h = fnv1a(h, &d.images[i].width, 4);
+    h = fnv1a(h, &d.images[i].height, 4);
+    if (d.images[i].rgb) h = fnv1a(h, d.images[i].rgb, size_t(d.images[i].width) * d.images[i].height * 3);
+  }
+  return h;
+}
+// Reads `path` into `sums`; returns the samples per pixel it holds, 0 when there is no file, and exits loudly when
+// the file belongs to another scene / camera / sample count (continuing it would silently mix two images).
+inline int checkpoint_load(const char* path, const checkpoint_header& want, std::vector<int64_t>& sums) {
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) return 0;
+  checkpoint_header h;
+  const bool head = std::fread(&h, sizeof h, 1, f) == 1;
+  const bool match = head && std::memcmp(h.magic, want.magic, 8) == 0 && h.version == want.version && h.width == want.width && h.height == want.height &&
+                     h.spp_total == want.spp_total && h.max_depth == want.max_depth && h.seed == want.seed && h.scene_hash == want.scene_hash &&
+                     h.spp_done <= h.spp_total;
+  const bool body = match && std::fread(sums.data(), 8, sums.size(), f) == sums.size();
+  std::fclose(f);
+  if (!body) {
+    std::fprintf(stderr, "rtb200: checkpoint %s %s; remove it to start over.\n", path,
+                 !head ? "is truncated" : (!match ? "was written for another scene, camera or sample count" : "is truncated"));
+    std::exit(1);
+  }
+  return int(h.spp_done);
+}
+inline void checkpoint_save(const char* path, checkpoint_header h, int spp_done, const std::vector<int64_t>& sums) {
+  h.spp_done = uint32_t(spp_done);
+  const std::string tmp = std::string(path) + ".tmp";  // write-then-rename: a kill mid-write leaves the old file intact
+  std::FILE* f = std::fopen(tmp.c_str(), "wb");
+  bool ok = f != nullptr;
+  if (f) {
+    ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(sums.data(), 8, sums.size(), f) == sums.size();
+    ok = (std::fclose(f) == 0) && ok;
+  }
+  if (!ok || std::rename(tmp.c_str(), path) != 0) {
+    std::fprintf(stderr, "rtb200: could not write checkpoint %s\n", path);
+    std::exit(1);
+  }
+}
 }  // namespace rtb200
 
+// Environment (the reference's camera has no such fields, and the drop-in keeps its class as it is):
+//   RT_B200_DEVICES         comma-separated CUDA ordinals (default "0"); samples are sharded over them
+//   RT_B200_P6              path of a binary P6 copy of the image
+//   RT_B200_CHECKPOINT      path of a checkpoint file: resumed when present, rewritten after every pass
+//   RT_B200_CHECKPOINT_SPP  samples per pixel per pass (default 256)
+//   RT_B200_STOP_AFTER_SPP  stop (exit code 3, no image) once that many samples are checkpointed — an interrupted run
 inline void camera::render(std::ostream& output_stream, const hittable& world) {
   rt_camera_desc cam = desc();
   rt_camera_frame frame;
@@ -930,8 +1010,6 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   auto scene = rtb200::flatten_world(world);
   rt_scene_desc sd = scene->desc();
 
-  // RT_B200_DEVICES = comma-separated CUDA ordinals (default "0"); samples are sharded
-  // over them and the int64 accumulators are summed on the first one.
   std::vector<int> devices;
   const char* env = std::getenv("RT_B200_DEVICES");
   std::string spec = env ? env : "0";
@@ -955,29 +1033,30 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   // Several devices: the exchange step (the per-pixel sum of camera.hpp:61) is done on the devices — every context
   // adds its accumulator into the first one's reduce buffer over peer memory (rt_render_opts.push_accum), no host sum.
   // Devices without peer access to the first one fall back to the exact integer sum on the host.
-  void* reduce = nullptr;
   bool on_device = R > 1;
-  if (R > 1) {
-    for (int r = 1; r < R && on_device; r++) on_device = rt_peer_enable(ctx[size_t(r)], ctx[0]) == RT_OK;
-    if (on_device) {
+  for (int r = 1; r < R && on_device; r++) on_device = rt_peer_enable(ctx[size_t(r)], ctx[0]) == RT_OK;
+
+  const size_t npix = size_t(frame.image_width) * frame.image_height;
+  std::vector<int64_t> host_sum;  // the pass's sums when the devices cannot reduce among themselves
+  // One pass = sample indices [begin, begin + count) of every pixel, count >= R, sharded over the devices.  Afterwards
+  // the pass's sums sit in the first context's accumulator or, without peer access, in host_sum.
+  auto run_pass = [&](int begin, int count) {
+    void* reduce = nullptr;
+    if (on_device) {  // (re-)zeroed for this pass
       int rc = rt_reduce_buffer(ctx[0], &cam, &reduce, nullptr);
       if (rc != RT_OK) rtb200::die(ctx[0], "rt_reduce_buffer", rc);
     }
-  }
-  for (int r = 0; r < R; r++) {  // asynchronous: all devices render concurrently
-    rt_render_opts o;
-    std::memset(&o, 0, sizeof o);
-    o.seed = 0;
-    o.sample_begin = int32_t((int64_t(samples_per_pixel) * r) / R);
-    o.sample_count = int32_t((int64_t(samples_per_pixel) * (r + 1)) / R) - o.sample_begin;
-    o.clear = 1;
-    o.push_accum = on_device ? reduce : nullptr;
-    int rc = rt_render(ctx[size_t(r)], &cam, &o);
-    if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_render", rc);
-  }
-  const size_t npix = size_t(frame.image_width) * frame.image_height;
-  std::vector<uint8_t> rgb(npix * 3);
-  if (R == 1 || on_device) {
+    for (int r = 0; r < R; r++) {  // asynchronous: all devices render concurrently
+      rt_render_opts o;
+      std::memset(&o, 0, sizeof o);
+      o.seed = 0;
+      o.sample_begin = begin + int32_t((int64_t(count) * r) / R);
+      o.sample_count = begin + int32_t((int64_t(count) * (r + 1)) / R) - o.sample_begin;
+      o.clear = 1;
+      o.push_accum = reduce;
+      int rc = rt_render(ctx[size_t(r)], &cam, &o);
+      if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_render", rc);
+    }
     if (on_device) {
       for (int r = 0; r < R; r++) {
         int rc = rt_synchronize(ctx[size_t(r)]);
@@ -985,22 +1064,75 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
       }
       int rc = rt_adopt_reduce_buffer(ctx[0]);
       if (rc != RT_OK) rtb200::die(ctx[0], "rt_adopt_reduce_buffer", rc);
+    } else if (R > 1) {
+      // exact integer reduction on the host side of the boundary (order-independent)
+      std::vector<int64_t> part(npix * 3);
+      host_sum.assign(npix * 3, 0);
+      for (int r = 0; r < R; r++) {
+        int rc = rt_download(ctx[size_t(r)], RT_BUF_ACCUM_I64, samples_per_pixel, part.data(), part.size() * 8);
+        if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_download", rc);
+        for (size_t i = 0; i < host_sum.size(); i++) host_sum[i] += part[i];
+      }
     }
+  };
+
+  const char* ckpt = std::getenv("RT_B200_CHECKPOINT");
+  if (ckpt && !*ckpt) ckpt = nullptr;
+  bool sums_on_host = false;
+  if (!ckpt) {
+    run_pass(0, samples_per_pixel);
+    sums_on_host = R > 1 && !on_device;
+  } else {
+    rtb200::checkpoint_header head;
+    std::memset(&head, 0, sizeof head);
+    std::memcpy(head.magic, "RTB2CKPT", 8);
+    head.version = 1, head.width = uint32_t(frame.image_width), head.height = uint32_t(frame.image_height);
+    head.spp_total = uint32_t(samples_per_pixel), head.max_depth = uint32_t(max_depth);
+    head.seed = 0, head.scene_hash = rtb200::scene_hash(sd, cam);
+    const char* e_pass = std::getenv("RT_B200_CHECKPOINT_SPP");
+    const char* e_stop = std::getenv("RT_B200_STOP_AFTER_SPP");
+    const int per_pass = std::max(R, e_pass ? std::atoi(e_pass) : 256);
+    const int stop_after = e_stop ? std::atoi(e_stop) : 0;
+    host_sum.assign(npix * 3, 0);
+    std::vector<int64_t> total(npix * 3, 0), part(npix * 3);
+    int done = rtb200::checkpoint_load(ckpt, head, total);
+    while (done < samples_per_pixel) {
+      int n = std::min(per_pass, samples_per_pixel - done);
+      if (samples_per_pixel - done - n < R) n = samples_per_pixel - done;  // no pass smaller than the device count
+      run_pass(done, n);
+      const int64_t* pass = host_sum.data();
+      if (R == 1 || on_device) {
+        int rc = rt_download(ctx[0], RT_BUF_ACCUM_I64, samples_per_pixel, part.data(), part.size() * 8);
+        if (rc != RT_OK) rtb200::die(ctx[0], "rt_download", rc);
+        pass = part.data();
+      }
+      for (size_t i = 0; i < total.size(); i++) total[i] += pass[i];
+      done += n;
+      rtb200::checkpoint_save(ckpt, head, done, total);
+      std::printf("\rSamples remaining: %d ", samples_per_pixel - done);
+      std::fflush(stdout);
+      if (stop_after > 0 && done >= stop_after && done < samples_per_pixel) {
+        for (int r = 0; r < R; r++) rt_shutdown(ctx[size_t(r)]);
+        std::printf("\rStopped after %d of %d samples per pixel; checkpoint in %s\n", done, samples_per_pixel, ckpt);
+        std::exit(3);
+      }
+    }
+    host_sum.swap(total);
+    // write_color on the device from the restored sums — the same finalize kernel as an uninterrupted render
+    int rc = rt_upload_accum(ctx[0], &cam, host_sum.data(), host_sum.size() * 8);
+    if (rc != RT_OK) rtb200::die(ctx[0], "rt_upload_accum", rc);
+  }
+
+  std::vector<uint8_t> rgb(npix * 3);
+  if (!sums_on_host) {
     int rc = rt_download(ctx[0], RT_BUF_RGB8, samples_per_pixel, rgb.data(), rgb.size());
     if (rc != RT_OK) rtb200::die(ctx[0], "rt_download", rc);
   } else {
-    // exact integer reduction on the host side of the boundary (order-independent)
-    std::vector<int64_t> total(npix * 3, 0), part(npix * 3);
-    for (int r = 0; r < R; r++) {
-      int rc = rt_download(ctx[size_t(r)], RT_BUF_ACCUM_I64, samples_per_pixel, part.data(), part.size() * 8);
-      if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_download", rc);
-      for (size_t i = 0; i < total.size(); i++) total[i] += part[i];
-    }
     // write_color (common/color.hpp:26-58) in double, operation for operation what the device's finalize kernel does
     const double scale = double(1.0f / float(samples_per_pixel));  // pixel_samples_scale, camera.hpp:83
     const double hi = double(0.999f);
-    for (size_t i = 0; i < total.size(); i++) {
-      const double lin = double(total[i]) * (1.0 / 4294967296.0) * scale;
+    for (size_t i = 0; i < host_sum.size(); i++) {
+      const double lin = double(host_sum[i]) * (1.0 / 4294967296.0) * scale;
       double g = lin > 0.0 ? std::sqrt(lin) : 0.0;
       g = g < 0.0 ? 0.0 : (g > hi ? hi : g);
       rgb[i] = uint8_t(int(256 * g));
@@ -1009,6 +1141,10 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   for (int r = 0; r < R; r++) rt_shutdown(ctx[size_t(r)]);
 
   rtb200::write_ppm_p3(output_stream, frame.image_width, frame.image_height, rgb.data());
+  if (const char* p6 = std::getenv("RT_B200_P6")) {
+    if (*p6 && !rtb200::write_ppm_p6(p6, frame.image_width, frame.image_height, rgb.data()))
+      std::fprintf(stderr, "rtb200: could not write %s\n", p6);
+  }
   std::printf("\rDone.                       \n");
   std::fflush(stdout);
 }

@@ -339,3 +339,71 @@ def test_render_option_errors(rtb, gpu_ctx):
         gpu_ctx.adopt_reduce_buffer()  # the reduce buffer was made for the 32-wide camera
     gpu_ctx.render(cam, seed=1)  # still usable afterwards
     assert gpu_ctx.stats().samples == 32 * 32 * 4
+
+
+def test_upload_accum_resumes_a_render(rtb, gpu_ctx):
+    """rt_upload_accum is the inverse of rt_download(ACCUM_I64): sums saved after samples [0, 20), restored into a
+    fresh accumulator and continued with [20, 40) give the bits of the uninterrupted 40-sample render
+    (camera.hpp:55-61 is a plain sum; the device keeps it in integers)."""
+    sc = rtb.Scene("cornell_smoke", rand_seed=1)
+    cam = sc.camera_copy(image_width=72, samples_per_pixel=40)
+    gpu_ctx.upload_scene(sc.desc)
+    gpu_ctx.render(cam, seed=5)
+    whole = gpu_ctx.download_accum().copy()
+    rgb = gpu_ctx.download_rgb8(40).copy()
+    gpu_ctx.render(cam, seed=5, sample_begin=0, sample_count=20)
+    saved = gpu_ctx.download_accum().copy()
+    gpu_ctx.render(cam, seed=9, sample_begin=0, sample_count=3)  # the accumulator now holds something else
+    gpu_ctx.upload_accum(cam, saved)
+    assert np.array_equal(gpu_ctx.download_accum(), saved)
+    gpu_ctx.render(cam, seed=5, sample_begin=20, sample_count=20, clear=False)
+    assert np.array_equal(gpu_ctx.download_accum(), whole)
+    assert np.array_equal(gpu_ctx.download_rgb8(40), rgb)
+    with pytest.raises(rtb.RtError):  # wrong size
+        gpu_ctx.upload_accum(cam, saved[:-1])
+    other = rtb.Context(0)  # a context that never rendered can be restored into and finalised
+    other.upload_accum(cam, whole)
+    assert np.array_equal(other.download_rgb8(40), rgb)
+    other.close()
+
+
+def test_cpp_checkpointed_render_and_p6(rtb, gpu_ctx, tmp_path):
+    """The C++ host's progressive mode (RT_B200_CHECKPOINT*): passes of 7 spp, an interruption after 14, a resume on
+    another number of 'devices' — the P3 text equals the uninterrupted render's, and RT_B200_P6 writes the same bytes
+    in binary.  A checkpoint of another camera is refused."""
+    import os
+    import subprocess
+
+    host = os.path.join(rtb.REPO_ROOT, "raytracing-practice_b200", "host")
+    exe = str(tmp_path / "dropin")
+    libdir = os.path.dirname(rtb.CUDA_LIB_PATH)
+    cmd = ["g++", "-std=c++11", "-O1", "-I", host, "-I", os.path.join(rtb.REPO_ROOT, "include"),
+           os.path.join(rtb.REPO_ROOT, "tests", "cpp", "dropin_main.cpp"), "-L", libdir, "-lrt_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    base = {k: v for k, v in os.environ.items() if not k.startswith("RT_B200_")}
+
+    def run(out, env, spp="33"):
+        return subprocess.run([exe, "simple_light", out, "80", spp], capture_output=True, text=True, env=dict(base, **env))
+
+    one, p6 = str(tmp_path / "one.ppm"), str(tmp_path / "one.p6")
+    r = run(one, {"RT_B200_P6": p6})
+    assert r.returncode == 0, r.stderr[-2000:]
+    tok = open(one).read().split()
+    w, h = int(tok[1]), int(tok[2])
+    raw = open(p6, "rb").read()
+    head = b"P6\n%d %d\n255\n" % (w, h)
+    assert raw.startswith(head) and len(raw) == len(head) + w * h * 3
+    assert np.array_equal(np.frombuffer(raw[len(head):], np.uint8), np.array(tok[4:], dtype=np.uint8))
+
+    ck, part, two = str(tmp_path / "render.ckpt"), str(tmp_path / "part.ppm"), str(tmp_path / "two.ppm")
+    r = run(part, {"RT_B200_CHECKPOINT": ck, "RT_B200_CHECKPOINT_SPP": "7", "RT_B200_STOP_AFTER_SPP": "14"})
+    assert r.returncode == 3 and "Stopped after 14 of 33" in r.stdout, (r.returncode, r.stdout, r.stderr[-2000:])
+    assert os.path.getsize(ck) == 48 + w * h * 3 * 8
+    r = run(two, {"RT_B200_CHECKPOINT": ck, "RT_B200_CHECKPOINT_SPP": "7"}, spp="32")  # another sample count: refused
+    assert r.returncode == 1 and "another scene, camera or sample count" in r.stderr
+    r = run(two, {"RT_B200_CHECKPOINT": ck, "RT_B200_CHECKPOINT_SPP": "8", "RT_B200_DEVICES": "0,0,0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(two).read() == open(one).read()
+    r = run(two, {"RT_B200_CHECKPOINT": ck})  # a finished checkpoint: nothing left to render, same image
+    assert r.returncode == 0 and open(two).read() == open(one).read()
