@@ -387,6 +387,9 @@ constexpr int kTravDone = int(0x80000000u);
 #ifndef RT_NODE_THR
 #define RT_NODE_THR 1
 #endif
+#ifndef RT_SPECULATIVE
+#define RT_SPECULATIVE 0  // 1: speculative while-while (node_step_spec); measured 0.88x on book2_final, 0.96-1.00x elsewhere (gpurun_out/ab_spec.log)
+#endif
 #ifndef RT_NODE_UNROLL
 #define RT_NODE_UNROLL 2  // node steps per warp vote: +3..5 % on the BVH-heavy scenes, -4 % on 2-node Cornell trees (gpurun_out/ab_unroll.log)
 #endif
@@ -515,12 +518,53 @@ __device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const Nod
   return trav_pop(ts, st);
 }
 
+// Speculative variant (Aila & Laine's "speculative while-while"): a lane that reaches a leaf while its postponed-leaf
+// slot `pend` is free parks the leaf there and keeps walking, so it stays useful in the node loop instead of idling
+// until the slowest lane finds a leaf.  The nodes it visits meanwhile are culled against the closest hit BEFORE the
+// parked leaf is intersected — extra visits, never a different answer (a subtree culled later starts beyond best.t).
+template <bool COUNT, bool ALL_SMEM = false>
+__device__ __forceinline__ void node_step_spec(TravState& ts, TravStack& st, const NodeSource& ns, int& pend, unsigned int* cn) {
+  float4 a, b, c;
+  int c0, c1;
+  load_node<ALL_SMEM>(ns, ts.cur, a, b, c, c0, c1);
+  if (COUNT) cn[CN_NODE]++;
+  const float3 inv = ts.inv, ood = ts.ood;
+  float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
+  float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
+  float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
+  float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+  float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
+  y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
+  z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
+  float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+  float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  const bool h0 = n0 <= f0, h1 = n1 <= f1;
+  // (written branch by branch like node_step: folding both cases into one `first0 = h0 && (!h1 || n0 <= n1)` made
+  //  nvcc 12.9 push the SAME child it descends into — st.local of c1 unconditionally in the PTX)
+  int next = kTravDone;
+  if (h0 && h1) {
+    const bool first0 = n0 <= n1;
+    st.node[ts.sp] = first0 ? c1 : c0;
+    st.t[ts.sp] = first0 ? n1 : n0;
+    ts.sp++;
+    next = first0 ? c0 : c1;
+  } else if (h0 || h1) {
+    next = h0 ? c0 : c1;
+  }
+  if (next >= 0 || (next != kTravDone && pend != kTravDone)) {  // a node, or a leaf while the parking slot is taken
+    ts.cur = next;
+    return;
+  }
+  if (next != kTravDone) pend = next;  // park the leaf, carry on with the stack
+  trav_pop(ts, st);
+}
+
 // leaf: ~cur = (first << 3) | (count - 1)
 // `key_of(key, bounce)` yields the ray's Philox counter; it is only called when a medium is actually sampled
 template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn>
-__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
-                                         const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
-  const int code = ~ts.cur;
+__device__ __forceinline__ void leaf_body(TravState& ts, int leaf, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn, const LeafSource& ls) {
+  const int code = ~leaf;
   const int first = code >> 3, count = (code & 7) + 1;
   const float3 o = ts.o, d = ts.d;
   for (int k = 0; k < count; k++) {
@@ -564,6 +608,11 @@ __device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, con
     }
     if (t != -1.0f) ts.best = Hit{t, ref};
   }
+}
+template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn>
+__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
+                                         const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
+  leaf_body<COUNT, CALLFREE, STAGED>(ts, ts.cur, sc, media, key_of, cn, ls);
   return trav_pop(ts, st);
 }
 
@@ -629,7 +678,29 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
   ts.best = Hit{tmax, REF_NONE};
   ts.cur = kTravDone;
   if (active) trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
-#if RT_NODE_THR == 1
+#if RT_SPECULATIVE
+  int pend = kTravDone;  // the parked leaf, kTravDone = none
+  for (;;) {
+    while (__any_sync(FULL, ts.cur >= 0)) {
+#pragma unroll
+      for (int u = 0; u < RT_NODE_UNROLL; u++)
+        if (ts.cur >= 0) node_step_spec<COUNT, ALL_SMEM>(ts, st, ns, pend, cn);
+    }
+    // every lane: cur is a leaf or finished, pend a parked (nearer) leaf or none
+    const bool parked = pend != kTravDone;
+    const int leaf = parked ? pend : ts.cur;
+    if (!__any_sync(FULL, leaf != kTravDone)) break;
+    if (leaf != kTravDone) {
+      leaf_body<COUNT, false, ALL_SMEM>(ts, leaf, sc, media, [&](PathKey& k, uint32_t& b) { k = key, b = bounce; }, cn, ls);
+      const int second = ts.cur;
+      pend = kTravDone;
+      if (second != kTravDone) {  // a second leaf moves up to the parking slot; the lane walks on from the stack
+        if (parked) pend = second;
+        trav_pop(ts, st);
+      }
+    }
+  }
+#elif RT_NODE_THR == 1
   // classic while-while with the lane's mode read off ts.cur (>= 0: node, kTravDone: finished, else a leaf): the
   // node loop drains to the last lane — one vote per step —, then the leaves are intersected together
   for (;;) {
