@@ -376,7 +376,9 @@ def main():
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp32_peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     kernel_rays_s = rays_per_step / world / (ms_per_step * 1e-3)  # one launch = one rank's kernel
-    roofline = {"bound": "fp32-issue (not hbm, not tensor: the whole scene is L1/shared resident; SURVEY.md 8(d))",
+    roofline = {"bound": "fp32",
+                "bound_note": "FP32/ALU issue under divergence - neither hbm nor tensor: the whole scene is shared-memory / L1 resident and the algorithm "
+                              "has no dense contraction (SURVEY.md 8(d)); the hbm view of the same launch is in roofline.hbm",
                 "achieved": kernel_rays_s * census["flops_per_ray"] / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                 "frac": kernel_rays_s * census["flops_per_ray"] / 1e12 / fp32_peak_tflops,
                 "traffic": NCU_DRAM_BYTES_PER_SAMPLE * W * H * count,

@@ -669,6 +669,10 @@ int rt_init(int device, rt_ctx** out) {
   auto bail = [&](const char* what, cudaError_t err) {
     std::lock_guard<std::mutex> g(g_err_mutex);
     g_init_error = std::string(what) + ": " + cudaGetErrorString(err);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RT_ERR_CUDA;
   };
@@ -796,7 +800,7 @@ static int ensure_accum(rt_ctx* ctx, int W, int H, bool clear) {
   size_t values = size_t(W) * H * 3;
   if (values != ctx->accum_values || ctx->acc_w != W) {
     cudaFree(ctx->accum);
-    ctx->accum = nullptr;
+    ctx->accum = nullptr, ctx->accum_values = 0, ctx->acc_w = ctx->acc_h = 0;  // a failed cudaMalloc below must not leave the old size behind
     RT_CUDA(ctx, cudaMalloc(&ctx->accum, values * 8));
     ctx->accum_values = values;
     ctx->acc_w = W, ctx->acc_h = H;
