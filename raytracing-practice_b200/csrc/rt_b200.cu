@@ -479,7 +479,13 @@ struct rt_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   std::string error;
-  std::vector<void*> scene_allocs;
+  // the device scene lives in ONE grow-only arena filled by ONE copy from a pinned staging buffer: re-uploading a scene
+  // (bench.py's e2e does it every step) then makes no cudaMalloc / cudaFree at all — those calls synchronise the device
+  // and took 60-500 ms per upload inside a process that also holds torch's allocations (gpurun_out/bench_n1_final4.json)
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  unsigned char* staging = nullptr;  // cudaHostAlloc
+  size_t staging_bytes = 0;
   DeviceScene sc;
   bool has_scene = false;
   HostScene host;
@@ -525,25 +531,49 @@ static int fail(rt_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
-template <typename T>
-static int upload(rt_ctx* ctx, const std::vector<T>& v, const T** out) {
-  *out = nullptr;
-  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  void* p = nullptr;
-  RT_CUDA(ctx, cudaMalloc(&p, bytes));
-  ctx->scene_allocs.push_back(p);
-  if (!v.empty()) RT_CUDA(ctx, cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  *out = static_cast<const T*>(p);
+namespace {
+struct ScenePiece {
+  const void* src;
+  size_t bytes;
+  void* field;  // address of the DeviceScene pointer member this array is published through
+  size_t offset;
+};
+}  // namespace
+
+// Packs the pieces (256-byte aligned) into the pinned staging buffer, copies them to the arena in one H2D transfer and
+// publishes the device pointers.  Both buffers only ever grow.
+static int upload_pieces(rt_ctx* ctx, std::vector<ScenePiece>& pieces) {
+  size_t total = 0;
+  for (ScenePiece& p : pieces) {
+    p.offset = total;
+    total += (std::max<size_t>(p.bytes, 1) + 255) & ~size_t(255);
+  }
+  if (total > ctx->arena_bytes) {
+    const size_t want = total + total / 2;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->arena);
+    ctx->arena = nullptr, ctx->arena_bytes = 0;
+    RT_CUDA(ctx, cudaMalloc(&ctx->arena, want));
+    ctx->arena_bytes = want;
+  }
+  if (total > ctx->staging_bytes) {
+    const size_t want = total + total / 2;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost(ctx->staging);
+    ctx->staging = nullptr, ctx->staging_bytes = 0;
+    RT_CUDA(ctx, cudaHostAlloc(&ctx->staging, want, cudaHostAllocDefault));
+    ctx->staging_bytes = want;
+  }
+  for (const ScenePiece& p : pieces) {
+    if (p.bytes) std::memcpy(ctx->staging + p.offset, p.src, p.bytes);
+    const void* dev = ctx->arena + p.offset;
+    std::memcpy(p.field, &dev, sizeof dev);
+  }
+  RT_CUDA(ctx, cudaMemcpyAsync(ctx->arena, ctx->staging, total, cudaMemcpyHostToDevice, ctx->stream));
   return RT_OK;
 }
 
-static void free_scene(rt_ctx* ctx) {
-  for (size_t i = 0; i < ctx->scene_allocs.size(); i++) {
-    cudaError_t e = cudaFree(ctx->scene_allocs[i]);
-    if (e != cudaSuccess && std::getenv("RT_B200_DEBUG"))
-      std::fprintf(stderr, "[rt_b200] free_scene: cudaFree(alloc #%zu = %p) -> %s\n", i, ctx->scene_allocs[i], cudaGetErrorString(e));
-  }
-  ctx->scene_allocs.clear();
+static void free_scene(rt_ctx* ctx) {  // the arena stays: the next rt_upload_scene overwrites it
   ctx->has_scene = false;
 }
 
@@ -696,6 +726,8 @@ void rt_shutdown(rt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_scene(ctx);
+  cudaFree(ctx->arena);
+  cudaFreeHost(ctx->staging);
   cudaFree(ctx->accum);
   cudaFree(ctx->pool_cold);
   cudaFree(ctx->reduce_buf);
@@ -729,9 +761,8 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   if (h.bvh_depth > kStackDepth) return fail(ctx, RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
   if (h.leaf_refs.size() >= (size_t(1) << 27)) return fail(ctx, RT_ERR_UNSUPPORTED, "too many leaf references for the 32-bit leaf code");
   DeviceScene& s = ctx->sc;
-  int rc;
-#define UP(field, vec) \
-  if ((rc = upload(ctx, vec, &s.field)) != RT_OK) return rc;
+  std::vector<ScenePiece> pieces;
+#define UP(field, vec) pieces.push_back(ScenePiece{vec.data(), vec.size() * sizeof(vec[0]), &s.field, 0});
   UP(nodes, h.nodes)
   UP(leaf_refs, h.leaf_refs)
   UP(spheres, h.spheres)
@@ -754,6 +785,8 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   UP(xops, h.xops)
   UP(xchains, h.xchains)
 #undef UP
+  int rc = upload_pieces(ctx, pieces);
+  if (rc != RT_OK) return rc;
   s.n_nodes = int(h.nodes.size() / 4);
   s.n_spheres = int(h.spheres.size() / 2);
   s.n_quads = int(h.quads.size() / 3);
