@@ -46,6 +46,7 @@ struct RenderParams {
   unsigned long long n_values;   // 3 * W * H
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
+  unsigned int state_off;  // byte offset of the per-thread shade-state records in dynamic shared memory
   float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
 };
 
@@ -53,9 +54,6 @@ struct RenderParams {
 #define RT_THREADS 896  // 28 warps x 72 registers: +6 % over 1024 x 64 on the Book-2 scene since the box primitive (gpurun_out/ab_threads.log)
 #endif
 constexpr int kRenderThreads = RT_THREADS;
-#ifndef RT_OUTLINED_TRAVERSAL
-#define RT_OUTLINED_TRAVERSAL 0
-#endif
 #ifndef RT_DEFAULT_POOL
 #define RT_DEFAULT_POOL 0
 #endif
@@ -89,10 +87,6 @@ __global__ void push_kernel(const unsigned long long* __restrict__ accum, unsign
 template <bool COUNT, bool ALL_SMEM>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
-#if RT_OUTLINED_TRAVERSAL
-  __shared__ DeviceScene s_sc;  // closest_hit_outlined cannot address the kernel's constant bank
-  for (int i = threadIdx.x; i < int(sizeof(DeviceScene) / 4); i += blockDim.x) reinterpret_cast<int*>(&s_sc)[i] = reinterpret_cast<const int*>(&P.sc)[i];
-#endif
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
   LeafSource ls{0u, 0u, 0u};
   if (ALL_SMEM) {  // ... and the leaves' data: [nodes][spheres 2 x float4][boxes 3 x float4][leaf refs u32]
@@ -111,19 +105,26 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
 
-  // Per-lane path state, kept small on purpose: the kernel runs 896 threads per SM (72 registers); 1024 x 64 was
-  // best before the box primitive grew the leaf code, 512 x 128 is 9-23 % slower (tools/ab_variants.py).
-  unsigned int item = blockIdx.x * blockDim.x + threadIdx.x;  // n_items < 2^32 is checked by the host
-  int pixel = -1, s = 0, s_end = 0;
+  // Per-lane path state, kept small on purpose: the kernel runs 896 threads per SM (72 registers; 1024 x 64 and 768 x 80
+  // are slower, gpurun_out/ab_lean2.log) and it is very sensitive to what is live across the traversal — two more
+  // values cost 16-24 % (profiles/r15_fastforward_rejected.patch), the diet below gained 6-9 % (gpurun_out/ab_lean*.log):
+  // no running radiance sum, a warp-uniform ray counter, no end-of-item / next-item registers, and
+  // what only SHADE needs — throughput, depth, pixel, next sample — lives in shared memory between shades, not in
+  // registers across the traversal: two float4 records per thread, {beta.xyz, depth} and {pixel, s, -, -}, read with
+  // volatile LDS.128 so that the compiler cannot carry a loaded value across the traversal instead.
+  const uint32_t st_a = opaque_u32(uint32_t(__cvta_generic_to_shared(s_nodes)) + P.state_off) + 16u * threadIdx.x;
+  constexpr uint32_t kStB = 16u * kRenderThreads;
+  auto sts_f4 = [](uint32_t addr, float4 v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); };
+  sts_f4(st_a, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0)));
+  sts_f4(st_a + kStB, make_float4(__int_as_float(-1), __int_as_float(P.sample_begin), 0.0f, 0.0f));
+  const int s_last = P.sample_begin + P.sample_count;
   bool alive = false;
   unsigned int n_rays = 0;
   unsigned int cn[COUNT ? CN_COUNT : 1];
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++) cn[i] = 0;
-  PathKey key{P.key, 0u, 0u};
-  float3 o = f3(0, 0, 0), d = f3(0, 0, 1), beta = f3(1, 1, 1), L = f3(0, 0, 0);
+  float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
   float time = 0.0f;
-  int depth = 0;
   uint32_t skip = REF_NONE;
 
   // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
@@ -138,18 +139,24 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   bool done = false;
   for (;;) {
     if (!alive && !done) {
-      if (s == s_end) {
+      const float4 B0 = lds_f4(st_a + kStB);
+      int pixel = __float_as_int(B0.x), s = __float_as_int(B0.y);
+      PathKey key{P.key, uint32_t(pixel), 0u};
+      // a work item holds a power-of-two number of samples (the host rounds P.chunk down): "my item is used up" is a
+      // mask test on the next sample index — no end-of-item register; initially s == sample_begin, which reads as used up
+      if ((((unsigned)(s - P.sample_begin)) & (unsigned)(P.chunk - 1)) == 0u || s >= s_last) {
         done = true;
-        while (item < P.n_items) {
+        for (;;) {
+          const unsigned long long it = atomicAdd(P.counters, 1ull);  // taken when needed: no prefetched candidate to keep
+          if (it >= (unsigned long long)P.n_items) break;
+          const unsigned int item = (unsigned int)it;
           const unsigned int chunk = item / P.per_chunk, q = item - chunk * P.per_chunk;
           const unsigned int tile = q >> 5, lane = q & 31u;
           const int px = int(tile % (unsigned)P.tiles_x) * 8 + int(lane & 7u);
           const int py = int(tile / (unsigned)P.tiles_x) * 4 + int(lane >> 3);
-          item = (unsigned int)atomicAdd(P.counters, 1ull);  // my next candidate
           if (px < P.cam.W && py < P.cam.H) {
             s = P.sample_begin + int(chunk) * P.chunk;
-            s_end = min(s + P.chunk, P.sample_begin + P.sample_count);
-            if (s < s_end) {
+            if (s < s_last) {
               pixel = py * P.cam.W + px;
               key.pixel = uint32_t(pixel);
               done = false;
@@ -176,28 +183,37 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
           dir = dir - off;
         }
         d = dir;
-        beta = f3(1.0f, 1.0f, 1.0f);
-        L = f3(0.0f, 0.0f, 0.0f);
-        depth = P.cam.max_depth;
+        sts_f4(st_a, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(P.cam.max_depth)));
+        sts_f4(st_a + kStB, make_float4(__int_as_float(pixel), __int_as_float(s), 0.0f, 0.0f));
         skip = REF_NONE;
-        alive = depth > 0;  // max_depth <= 0: ray_color returns black at once (camera.hpp:183-186)
+        alive = P.cam.max_depth > 0;
       }
     }
-    if (!__any_sync(FULL, alive)) {
+    const unsigned live = __ballot_sync(FULL, alive);
+    if (live == 0u) {
       if (__all_sync(FULL, done)) break;
       continue;
     }
+    n_rays += __popc(live);  // warp-uniform: the count lives in the uniform datapath, not in a lane register
     // ---- one segment of ray_color (camera.hpp:180-232) -----------------------------------
-    const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;  // Philox counter word: 1, 2, ...
-    if (alive) n_rays++;
-#if RT_OUTLINED_TRAVERSAL  // measured: -3 % (gpurun_out/ab_outlined.log); kept for the record
-    Hit h{INF, REF_NONE};
-    if (alive && media) h = sample_global_media<COUNT>(sc, o, d, time, 0.001f, INF, key, bounce, cn);
-    h = closest_hit_outlined<COUNT>(&s_sc, s_nodes, P.smem_nodes, o, d, time, skip, h, P.key, key.pixel, key.sample, bounce, alive, cn);
-#else
-    Hit h = closest_hit<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key, bounce, cn, alive, ls);
-#endif
+    // the ray's Philox counter, read back for the scene-enclosing media (every ray) and — lazily — for a medium leaf
+    auto key_of = [&](PathKey& k, uint32_t& b) {
+      const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
+      k = PathKey{P.key, uint32_t(__float_as_int(B.x)), uint32_t(__float_as_int(B.y) - 1)};
+      b = uint32_t(P.cam.max_depth - __float_as_int(A.w)) + 1u;
+    };
+    Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key_of, cn, alive, ls);
     if (alive) {
+      const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
+      float3 beta = f3(A.x, A.y, A.z);
+      int depth = __float_as_int(A.w);
+      const int pixel = __float_as_int(B.x);
+      const PathKey key{P.key, uint32_t(pixel), uint32_t(__float_as_int(B.y) - 1)};
+      const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;
+      // The radiance of a path is beta x (emission | background) at its LAST vertex: no material of the reference both
+      // emits and scatters (diffuse_light::scatter is false, material.hpp:36; every other emitted() is black), so no
+      // running sum lives across the traversal.
+      float3 L = f3(0.0f, 0.0f, 0.0f);
       if (h.ref == REF_NONE) {
         L = L + beta * P.cam.bg;
         alive = false;
@@ -213,6 +229,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
           d = d_out;
           skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
           alive = --depth > 0;
+          sts_f4(st_a, make_float4(beta.x, beta.y, beta.z, __int_as_float(depth)));
         } else {
           alive = false;
         }
@@ -231,7 +248,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   }
   // ---- counters: warp-reduce, one atomic per warp ---------------------------------------
   unsigned int rays = n_rays;
-  for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xFFFFFFFFu, rays, off);
   if ((threadIdx.x & 31) == 0) atomicAdd(P.counters + 1, (unsigned long long)rays);
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++)
@@ -904,6 +920,7 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   long long total = (long long)f.image_width * f.image_height * P.sample_count;
   long long chunk = total / (threads * 8);
   P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, 32, (long long)P.sample_count})));
+  while (P.chunk & (P.chunk - 1)) P.chunk &= P.chunk - 1;  // largest power of two below: the megakernel finds the end of an item with a mask
   P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
   const unsigned long long n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull * (unsigned long long)P.n_chunks;
   if (n_items >= 0xFFFFFFFFull - (unsigned long long)threads) return fail(ctx, RT_ERR_INVALID, "image x samples too large for one launch: shard the samples");
@@ -954,13 +971,21 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     // memory" (all BASELINE scenes): its node step then has neither the bounds test nor the global-memory path, and a
     // leaf visit makes no global load
     const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
-    const bool all_smem = staged + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
-    if (all_smem) P.smem_nodes = ctx->sc.n_nodes, smem = staged;
+    constexpr size_t kStateBytes = size_t(32) * kRenderThreads;  // per-thread shade state (render_kernel)
+    const bool all_smem = staged + kStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+    if (all_smem) {
+      P.smem_nodes = ctx->sc.n_nodes, smem = staged;
+    } else {  // the top of the BVH only, as much as fits beside the state records
+      P.smem_nodes = int(std::min<size_t>(size_t(P.smem_nodes), (ctx->smem_optin - 4096 - kStateBytes) / 64));
+      smem = size_t(P.smem_nodes) * 64;
+    }
+    P.state_off = unsigned((smem + 15) & ~size_t(15));
+    smem = P.state_off + kStateBytes;
     void (*kern)(RenderParams) = count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
                                        : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
     RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    // counters[0] = first item not pre-assigned to a thread
-    unsigned long long first = (unsigned long long)threads;
+    // counters[0] = next work item: lanes take items with atomicAdd when they need one
+    unsigned long long first = 0ull;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, launch_render(kern, grid, smem, ctx->stream, P));
     ctx->launches++;
