@@ -51,7 +51,7 @@ __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x);
                             // conservative default and costs +2.5..5 % of the whole render (gpurun_out/ab_philox.log)
 #endif
 #ifndef RT_OUTLINE_PHILOX
-#define RT_OUTLINE_PHILOX RT_OUTLINE
+#define RT_OUTLINE_PHILOX __forceinline__  // 4 call sites of ~45 instructions: inlined since the state diet (+1.3..2.2 %, gpurun_out/ab_phinl.log)
 #endif
 __device__ __forceinline__ uint4 philox4x32_10_inl(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -384,6 +384,9 @@ constexpr int kStackDepth = 32;
 // TravState::cur of a finished (or idle) traversal: negative like a leaf code, but no leaf code can have this value
 // (it would need 2^28 leaf references).  Lets a loop read the lane's mode off `cur` alone: >= 0 node, else leaf / done.
 constexpr int kTravDone = int(0x80000000u);
+#ifndef RT_GM_INLINE
+#define RT_GM_INLINE 0
+#endif
 #ifndef RT_GM_NOUNROLL
 #define RT_GM_NOUNROLL 1  // one medium_sample call site for the scene-enclosing media: +0.4..1.2 % (gpurun_out/ab_lean2.log)
 #endif
@@ -457,7 +460,11 @@ __device__ __forceinline__ Hit sample_global_media(const DeviceScene& sc, float3
   for (int g = 0; g < sc.n_global_media; g++) {
     const int mi = sc.global_media[g];
     const DMedium m = sc.media[mi];
+#if RT_GM_INLINE
+    float t = medium_sample_impl<true>(sc, m, mi, o, d, time, tmin, best.t, key, bounce);
+#else
     float t = medium_sample(sc, m, mi, o, d, time, tmin, best.t, key, bounce);
+#endif
     if (COUNT) cn[CN_MEDIUM]++;
     if (t != -1.0f) best = Hit{t, make_ref(REF_MEDIUM, uint32_t(mi))};
   }
