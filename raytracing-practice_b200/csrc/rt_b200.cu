@@ -110,13 +110,14 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   // values cost 16-24 % (profiles/r15_fastforward_rejected.patch), the diet below gained 6-9 % (gpurun_out/ab_lean*.log):
   // no running radiance sum, a warp-uniform ray counter, no end-of-item / next-item registers, and
   // what only SHADE needs — throughput, depth, pixel, next sample — lives in shared memory between shades, not in
-  // registers across the traversal: two float4 records per thread, {beta.xyz, depth} and {pixel, s, -, -}, read with
-  // volatile LDS.128 so that the compiler cannot carry a loaded value across the traversal instead.
+  // registers across the traversal, and so do the ray's time and the primitive it starts on, which only leaves look at:
+  // two float4 records per thread, {beta.xyz, depth} and {pixel, s, time, skip}, read with volatile LDS so that the
+  // compiler cannot carry a loaded value across the traversal instead.
   const uint32_t st_a = opaque_u32(uint32_t(__cvta_generic_to_shared(s_nodes)) + P.state_off) + 16u * threadIdx.x;
   constexpr uint32_t kStB = 16u * kRenderThreads;
   auto sts_f4 = [](uint32_t addr, float4 v) { asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); };
   sts_f4(st_a, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0)));
-  sts_f4(st_a + kStB, make_float4(__int_as_float(-1), __int_as_float(P.sample_begin), 0.0f, 0.0f));
+  sts_f4(st_a + kStB, make_float4(__int_as_float(-1), __int_as_float(P.sample_begin), 0.0f, __uint_as_float(REF_NONE)));
   const int s_last = P.sample_begin + P.sample_count;
   bool alive = false;
   unsigned int n_rays = 0;
@@ -124,8 +125,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   if (COUNT)
     for (int i = 0; i < CN_COUNT; i++) cn[i] = 0;
   float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
-  float time = 0.0f;
-  uint32_t skip = REF_NONE;
 
   // Every iteration = (regenerate dead lanes) + (one path segment for all lanes).  The iteration
   // boundary is a warp vote, so the 32 lanes reconverge here; lanes that ran out of work idle
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         const int py = pixel / P.cam.W, px = pixel - py * P.cam.W;
         uint4 r0 = rng_block(key, 0u, 0u);
         float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
-        time = u01(r0.z);
+        const float time = u01(r0.z);
         float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
         o = P.cam.center;
         if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
@@ -184,8 +183,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         }
         d = dir;
         sts_f4(st_a, make_float4(1.0f, 1.0f, 1.0f, __int_as_float(P.cam.max_depth)));
-        sts_f4(st_a + kStB, make_float4(__int_as_float(pixel), __int_as_float(s), 0.0f, 0.0f));
-        skip = REF_NONE;
+        sts_f4(st_a + kStB, make_float4(__int_as_float(pixel), __int_as_float(s), time, __uint_as_float(REF_NONE)));
         alive = P.cam.max_depth > 0;
       }
     }
@@ -202,12 +200,18 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
       k = PathKey{P.key, uint32_t(__float_as_int(B.x)), uint32_t(__float_as_int(B.y) - 1)};
       b = uint32_t(P.cam.max_depth - __float_as_int(A.w)) + 1u;
     };
-    Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, time, 0.001f, INF, skip, media, key_of, cn, alive, ls);
+    auto aux_of = [&](float& t, uint32_t& sk) {
+      float tt, ss;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tt), "=f"(ss) : "r"(st_a + kStB + 8u));
+      t = tt, sk = __float_as_uint(ss);
+    };
+    Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, 0.001f, INF, media, key_of, aux_of, cn, alive, ls);
     if (alive) {
       const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
       float3 beta = f3(A.x, A.y, A.z);
       int depth = __float_as_int(A.w);
       const int pixel = __float_as_int(B.x);
+      const float time = B.z;
       const PathKey key{P.key, uint32_t(pixel), uint32_t(__float_as_int(B.y) - 1)};
       const uint32_t bounce = uint32_t(P.cam.max_depth - depth) + 1u;
       // The radiance of a path is beta x (emission | background) at its LAST vertex: no material of the reference both
@@ -227,9 +231,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
           beta = beta * atten;
           o = sf.p;
           d = d_out;
-          skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
+          const uint32_t skip = (h.ref >> 30) == REF_MEDIUM ? REF_NONE : h.ref;
           alive = --depth > 0;
           sts_f4(st_a, make_float4(beta.x, beta.y, beta.z, __int_as_float(depth)));
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(st_a + kStB + 12u), "r"(skip) : "memory");
         } else {
           alive = false;
         }

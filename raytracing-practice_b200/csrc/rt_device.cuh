@@ -741,23 +741,26 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
   return ts.best;
 }
 
-// closest_hit for a caller that does not hold the ray's Philox counter in registers: `key_of(key, bounce)` fetches it
-// where a medium needs it — for the scene-enclosing media at the start (every ray of such a scene, warp converged), and
-// lazily for a medium leaf.
-template <bool COUNT, bool ALL_SMEM, typename KeyFn>
-__device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float time, float tmin, float tmax,
-                                                 uint32_t skip_ref, bool media, KeyFn key_of, unsigned int* cn, bool active, const LeafSource& ls) {
+// closest_hit for a caller that keeps as little as possible in registers across the traversal: `key_of(key, bounce)`
+// fetches the ray's Philox counter where a medium needs it — for the scene-enclosing media at the start (every ray of
+// such a scene, warp converged), and lazily for a medium leaf — and `aux_of(time, skip)` fetches the ray's time and the
+// primitive it starts on, which only the leaves (and the media) look at: the node loop carries neither.
+template <bool COUNT, bool ALL_SMEM, typename KeyFn, typename AuxFn>
+__device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float tmin, float tmax, bool media,
+                                                 KeyFn key_of, AuxFn aux_of, unsigned int* cn, bool active, const LeafSource& ls) {
   const unsigned FULL = 0xFFFFFFFFu;
   TravState ts;
   TravStack st;
   ts.best = Hit{tmax, REF_NONE};
   ts.cur = kTravDone;
   if (active) {
-    trav_set_ray(ts, o, d, time, tmin, skip_ref);
+    trav_set_ray(ts, o, d, 0.0f, tmin, REF_NONE);
     if (media && sc.n_global_media) {
       PathKey k;
-      uint32_t b;
+      uint32_t b, skip;
+      float time;
       key_of(k, b);
+      aux_of(time, skip);
       ts.best = sample_global_media<COUNT>(sc, o, d, time, tmin, tmax, k, b, cn);
     }
     ts.sp = 0;
@@ -770,7 +773,10 @@ __device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const No
         if (ts.cur >= 0) node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
     }
     if (!__any_sync(FULL, ts.cur != kTravDone)) break;
-    if (ts.cur != kTravDone) leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, key_of, cn, ls);
+    if (ts.cur != kTravDone) {
+      aux_of(ts.time, ts.skip);
+      leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, key_of, cn, ls);
+    }
   }
   return ts.best;
 }
