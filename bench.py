@@ -35,11 +35,11 @@ F_SHADE = dict(lambertian=15, metal=35, dielectric=60, light=0, isotropic=15, ch
 # bytes per unit (fp32 device layouts): BVH2 node with both child boxes 64 B, sphere 32 B, quad 48 B
 B_NODE, B_SPH, B_QUAD, B_TEXEL, B_PERLIN = 64, 32, 48, 4, 56 * 16 + 7 * 24
 B_BOXPRIM = 48
-# from the committed ncu capture profiles/r14_render_final.md (render_kernel, book2_final 800x800 x 256 spp):
-# dram__bytes_read.sum + dram__bytes_write.sum = 31.8 MB + 3.77 GB per 163.84 M samples (traversal-stack / spill
+# from the committed ncu capture profiles/r15_render_lean.md (render_kernel, book2_final 800x800 x 256 spp):
+# dram__bytes_read.sum + dram__bytes_write.sum = 33.0 MB + 1.376 GB per 163.84 M samples (traversal-stack / spill
 # write-backs; the scene itself is cache resident), issue-slot utilisation and active lanes per instruction
-NCU_DRAM_BYTES_PER_SAMPLE = (31.832576e6 + 3.770347e9) / (800 * 800 * 256)
-NCU_ISSUE_UTIL, NCU_LANES = 0.722, 9.78
+NCU_DRAM_BYTES_PER_SAMPLE = (33.013504e6 + 1.375699e9) / (800 * 800 * 256)
+NCU_ISSUE_UTIL, NCU_LANES = 0.750, 9.97
 
 
 def parse():
@@ -382,10 +382,10 @@ def main():
                 "achieved": kernel_rays_s * census["flops_per_ray"] / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                 "frac": kernel_rays_s * census["flops_per_ray"] / 1e12 / fp32_peak_tflops,
                 "traffic": NCU_DRAM_BYTES_PER_SAMPLE * W * H * count,
-                "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per sample (profiles/r14_render_final.md) x this launch's samples; "
+                "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per sample (profiles/r15_render_lean.md) x this launch's samples; "
                                 "stack/spill write-backs, not scene data (algorithmic bytes are served by shared memory / L1)",
                 "simt": {"issue_slot_utilisation": NCU_ISSUE_UTIL, "active_lanes_per_instruction": NCU_LANES,
-                         "lane_issue_frac": NCU_ISSUE_UTIL * NCU_LANES / 32, "source": "profiles/r14_render_final.md (ncu --set full)"},
+                         "lane_issue_frac": NCU_ISSUE_UTIL * NCU_LANES / 32, "source": "profiles/r15_render_lean.md (ncu --set full)"},
                 "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal max clock)",
                 "flops_per_ray": census["flops_per_ray"], "bytes_per_ray": census["bytes_per_ray"], "census_per_ray": census["per_ray"],
                 "hbm": {"bound": "hbm", "achieved": kernel_rays_s * census["bytes_per_ray"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
