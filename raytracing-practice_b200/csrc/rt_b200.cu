@@ -924,7 +924,9 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   // samples per work item: enough items (>= 8 per thread) for the dynamic balance, at most 32
   long long total = (long long)f.image_width * f.image_height * P.sample_count;
   long long chunk = total / (threads * 8);
-  P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, 32, (long long)P.sample_count})));
+  long long chunk_max = 32;
+  if (const char* e = std::getenv("RT_B200_CHUNK_MAX")) chunk_max = std::max(1, std::atoi(e));  // A/B knob (tools/ab_env.py)
+  P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, chunk_max, (long long)P.sample_count})));
   while (P.chunk & (P.chunk - 1)) P.chunk &= P.chunk - 1;  // largest power of two below: the megakernel finds the end of an item with a mask
   P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
   const unsigned long long n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull * (unsigned long long)P.n_chunks;
