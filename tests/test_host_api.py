@@ -172,3 +172,29 @@ def test_box_lists_are_recognised_only_when_they_are_boxes(rtb, built):
     assert boxes_of(two_materials)[0] == 0
     # a sheared "box" (parallelogram faces) is not axis-aligned
     assert boxes_of(lambda s, m: s.list([s.quad((0, 0, 0), (1, 0.2, 0), (0, 1, 0), m) for _ in range(6)]))[0] == 0
+
+
+def test_checkpoint_file_helpers(rtb, tmp_path):
+    """RT_B200_CHECKPOINT's file layer on the CPU: round trip, replacement, refusal of another render's file, and the
+    scene hash telling two cameras / scenes apart (the GPU side is tests/test_gpu_render.py::test_cpp_checkpointed_*)."""
+    import os
+    import subprocess
+
+    host = os.path.join(rtb.REPO_ROOT, "raytracing-practice_b200", "host")
+    libdir = os.path.dirname(rtb.CUDA_LIB_PATH)
+    exe = str(tmp_path / "ckpt_unit")
+    r = subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I", host, "-I", os.path.join(rtb.REPO_ROOT, "include"),
+                        os.path.join(rtb.REPO_ROOT, "tests", "cpp", "ckpt_unit.cpp"), "-L", libdir, "-lrt_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ck = str(tmp_path / "a.ckpt")
+    r = subprocess.run([exe, ck, "roundtrip"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert os.path.getsize(ck) == 48 + 5 * 3 * 3 * 8 and not os.path.exists(ck + ".tmp")
+    for mode in ("other_scene", "other_spp"):
+        r = subprocess.run([exe, ck, mode], capture_output=True, text=True)
+        assert r.returncode == 1 and "another scene, camera or sample count" in r.stderr
+    with open(ck, "r+b") as f:  # a truncated file is refused too
+        f.truncate(100)
+    r = subprocess.run([exe, ck, "same"], capture_output=True, text=True)
+    assert r.returncode == 1 and "truncated" in r.stderr
