@@ -33,6 +33,18 @@ struct CameraDev {
   int W, H, max_depth, defocus;
 };
 
+// Shared-memory plan of the streaming kernel (rt_stream.cuh), byte offsets into its dynamic shared memory.
+struct StreamLayout {
+  uint32_t node_plane;             // bytes per node plane = 16 * n_nodes: planes A, B, C at 0, 1x, 2x; the (child, child) pairs (8 B) at 3x
+  uint32_t off_sph, off_box, off_refs;
+  uint32_t off_slots, slot_plane;  // path pool: 4 planes of 16 B x n_slots
+  uint32_t off_stack;              // traversal stacks: [level][thread] x 4 B
+  uint32_t off_tq, off_sq, ring_mask;  // trace / shade queues: rings of (ring_mask + 1) 16-bit slot numbers
+  uint32_t off_ctl;
+  uint32_t n_slots;
+  uint32_t total;
+};
+
 struct RenderParams {
   DeviceScene sc;
   CameraDev cam;
@@ -48,6 +60,7 @@ struct RenderParams {
   int smem_nodes;
   unsigned int state_off;  // byte offset of the per-thread shade-state records in dynamic shared memory
   float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
+  StreamLayout sl;   // streaming kernel only
 };
 
 #ifndef RT_THREADS
@@ -58,6 +71,10 @@ constexpr int kRenderThreads = RT_THREADS;
 #define RT_DEFAULT_POOL 0
 #endif
 constexpr bool kDefaultPoolKernel = RT_DEFAULT_POOL != 0;
+#ifndef RT_DEFAULT_STREAM
+#define RT_DEFAULT_STREAM 0
+#endif
+constexpr bool kDefaultStreamKernel = RT_DEFAULT_STREAM != 0;
 #ifndef RT_POOL_SMEM_NODES
 #define RT_POOL_SMEM_NODES 256
 #endif
@@ -261,6 +278,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
 
 }  // namespace rtb200
 #include "rt_pool.cuh"
+#include "rt_stream.cuh"
 namespace rtb200 {
 
 // ---- write_color (common/color.hpp:26-58) on the device, in double like the reference ----
@@ -850,6 +868,34 @@ static void fill_camera(const rt_camera_desc* cam, const rt_camera_frame& f, Cam
   c.defocus = cam->defocus_angle > 0.0f ? 1 : 0;  // camera.hpp:155
 }
 
+// The streaming kernel's shared-memory plan for the uploaded scene; false when the scene does not fit it (the whole BVH
+// must be staged, child codes must fit 16 bits) — the megakernel then renders.
+static bool stream_layout(const rt_ctx* ctx, int bvh_depth, StreamLayout& L) {
+  const DeviceScene& sc = ctx->sc;
+  const int max_leaf_code = (sc.n_leaf_refs << 3) | 7;
+  if (sc.n_nodes > kStreamMaxCode || max_leaf_code > kStreamMaxCode) return false;
+  auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+  size_t off = 0;
+  L.node_plane = uint32_t(16u * size_t(sc.n_nodes));
+  off = up16(3 * size_t(L.node_plane) + 8 * size_t(sc.n_nodes));
+  L.off_sph = uint32_t(off), off = up16(off + 16 * size_t(sc.n_spheres));
+  L.off_box = uint32_t(off), off = up16(off + 48 * size_t(sc.n_boxes));
+  L.off_refs = uint32_t(off), off = up16(off + 4 * size_t(sc.n_leaf_refs));
+  L.n_slots = RT_STREAM_SLOTS;
+  L.slot_plane = 16u * L.n_slots;
+  L.off_slots = uint32_t(off), off += 4 * size_t(L.slot_plane);
+  const int levels = std::max(1, bvh_depth);  // a traversal never holds more postponed children than the tree has levels
+  L.off_stack = uint32_t(off), off += size_t(levels) * kStackStride;
+  uint32_t cap = 64;
+  while (cap < 2 * L.n_slots) cap *= 2;  // ring capacity >= 2 x slots: a position is never reused while its last reader still holds it
+  L.ring_mask = cap - 1;
+  L.off_tq = uint32_t(off), off += 2 * size_t(cap);
+  L.off_sq = uint32_t(off), off += 2 * size_t(cap);
+  L.off_ctl = uint32_t(off), off += SC_BYTES;
+  L.total = uint32_t(off);
+  return off + sizeof(RenderParams) + 2048 <= ctx->smem_optin;
+}
+
 static int ensure_accum(rt_ctx* ctx, int W, int H, bool clear) {
   size_t values = size_t(W) * H * 3;
   if (values != ctx->accum_values || ctx->acc_w != W) {
@@ -947,9 +993,31 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   if (const char* e = std::getenv("RT_B200_KERNEL")) pool = std::string(e) == "pool" ? true : (std::string(e) == "mega" ? false : pool);
   if (opts->flags & RT_RENDER_MEGAKERNEL) pool = false;
   if (opts->flags & RT_RENDER_POOL) pool = true;
+  // the streaming kernel (rt_stream.cuh) when the scene fits its shared-memory plan
+  bool stream = kDefaultStreamKernel && !pool;
+  if (const char* e = std::getenv("RT_B200_KERNEL")) stream = std::string(e) == "stream" ? true : (std::string(e) == "mega" || std::string(e) == "pool" ? false : stream);
+  if (opts->flags & (RT_RENDER_MEGAKERNEL | RT_RENDER_POOL)) stream = false;
+  if (opts->flags & RT_RENDER_STREAM) stream = true, pool = false;
+  StreamLayout SL;
+  std::memset(&SL, 0, sizeof SL);
+  if (stream && !stream_layout(ctx, ctx->host.bvh_depth, SL)) {
+    if (opts->flags & RT_RENDER_STREAM) return fail(ctx, RT_ERR_UNSUPPORTED, "the scene does not fit the streaming kernel's shared-memory plan");
+    stream = false;
+  }
   if (first_piece) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.cam.max_depth <= 0) {
     // ray_color returns black at once (camera.hpp:183-186): nothing to trace, the sums stay as they are
+  } else if (stream) {
+    P.sl = SL;
+    P.smem_nodes = ctx->sc.n_nodes;
+    smem = SL.total;
+    void (*kern)(RenderParams) = count ? stream_kernel<true> : stream_kernel<false>;
+    RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned long long first = 0ull;
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+    kern<<<grid, kStreamThreads, smem, ctx->stream>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
   } else if (pool) {
     // work items of a power-of-two number of samples (the kernel finds the end of an item with a mask)
     int c2 = 1;
@@ -1167,6 +1235,15 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
   unsigned long long c[32];
   RT_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost));
   out->rays = c[1];
+  if (c[19] && std::getenv("RT_B200_DEBUG")) {  // the streaming kernel's watchdog records (debug builds)
+    std::fprintf(stderr, "[rt_b200] stream watchdog: %llu reports\n", c[19]);
+    for (int k = 0; k < 3 && k < int(c[19]); k++) {
+      const unsigned long long* o = c + 20 + 4 * k;
+      std::fprintf(stderr, "  where %llu thread %llu cta %llu a %d b %d | tq_avail %d sq_avail %d | tq head %llu tail %llu sq head %llu tail %llu | dead %d\n", o[0] & 0xFF,
+                   (o[0] >> 8) & 0xFFFF, (o[0] >> 24) & 0xFFFF, int(o[0] >> 40), int(o[3] >> 32), int(unsigned(o[1])), int(unsigned(o[1] >> 32)), o[2] & 0xFFFF,
+                   (o[2] >> 16) & 0xFFFF, (o[2] >> 32) & 0xFFFF, (o[2] >> 48) & 0xFFFF, int(unsigned(o[3])));
+    }
+  }
   out->samples = ctx->samples_total;  // every sample of the requested range is rendered: W*H*count per launch
   for (int i = 0; i < CN_COUNT; i++) out->census[i] = c[4 + i];
   if (ctx->timed) {

@@ -20,6 +20,8 @@ if sys.argv[1] == "build":
         info = err.splitlines()[k[0] + 2].strip() if k else "?"
         spill = err.splitlines()[k[0] + 1 + 1 - 1].strip() if k else ""
         print(tag, p.returncode, info, "|", [l.strip() for l in err.splitlines()[k[0]+1:k[0]+3]][0] if k else "")
+        ks = [i for i, l in enumerate(err.splitlines()) if "stream_kernelILb0" in l and "Compiling" in l]
+        if ks: print("   stream:", err.splitlines()[ks[0] + 3].strip(), "|", err.splitlines()[ks[0] + 2].strip())
 elif sys.argv[1] == "run":
     if len(sys.argv) > 4:  # child: one variant
         sys.path.insert(0, ROOT)
