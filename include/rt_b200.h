@@ -215,10 +215,12 @@ enum {
   RT_RENDER_COUNTERS = 1,  /* instrumented kernel: also fills rt_stats.census (slower; not for timing) */
   RT_RENDER_MEGAKERNEL = 2, /* force the one-path-per-lane megakernel (render_kernel)               */
   RT_RENDER_POOL = 4,       /* force the per-warp path-pool kernel (pool_kernel); with neither bit the
-                               library picks (env RT_B200_KERNEL=mega|pool|stream overrides the default) */
-  RT_RENDER_STREAM = 8      /* force the streaming kernel (stream_kernel: CTA-wide ray queues, lanes refilled
+                               library picks (env RT_B200_KERNEL=mega|pool|stream|refill overrides the default) */
+  RT_RENDER_STREAM = 8,     /* force the streaming kernel (stream_kernel: CTA-wide ray queues, lanes refilled
                                mid-traversal); RT_ERR_UNSUPPORTED when the scene does not fit its
                                shared-memory plan                                                   */
+  RT_RENDER_REFILL = 16     /* force the in-place-refill kernel (refill_kernel: a lane keeps its path, the warp
+                               leaves the traversal to shade as soon as enough lanes have their answer)  */
 };
 
 /* Asynchronous on the context's stream.  Accumulates fixed-point (2^-32) int64 RGB

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -59,6 +60,7 @@ struct RenderParams {
   unsigned long long* counters;  // [0] next work item, [1] rays, [2] samples
   int smem_nodes;
   unsigned int state_off;  // byte offset of the per-thread shade-state records in dynamic shared memory
+  unsigned int stack_off;  // byte offset of the shared-memory traversal stacks (kernels instantiated with SSTACK)
   float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
   StreamLayout sl;   // streaming kernel only
 };
@@ -67,6 +69,13 @@ struct RenderParams {
 #define RT_THREADS 896  // 28 warps x 72 registers: +6 % over 1024 x 64 on the Book-2 scene since the box primitive (gpurun_out/ab_threads.log)
 #endif
 constexpr int kRenderThreads = RT_THREADS;
+#ifndef RT_SMEM_STACK_BUDGET_KB
+#define RT_SMEM_STACK_BUDGET_KB 164  // shared memory a launch may use and still take the stacks in: leaves L1 >= 64 KB of the 228 KB
+#endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 1  // traversal stacks in shared memory when the launch has the room (rt_device.cuh, TravStackS)
+#endif
+constexpr size_t kSmemStackBudget = size_t(RT_SMEM_STACK_BUDGET_KB) * 1024;
 #ifndef RT_DEFAULT_POOL
 #define RT_DEFAULT_POOL 0
 #endif
@@ -75,6 +84,10 @@ constexpr bool kDefaultPoolKernel = RT_DEFAULT_POOL != 0;
 #define RT_DEFAULT_STREAM 0
 #endif
 constexpr bool kDefaultStreamKernel = RT_DEFAULT_STREAM != 0;
+#ifndef RT_DEFAULT_REFILL
+#define RT_DEFAULT_REFILL 0
+#endif
+constexpr bool kDefaultRefillKernel = RT_DEFAULT_REFILL != 0;
 #ifndef RT_POOL_SMEM_NODES
 #define RT_POOL_SMEM_NODES 256
 #endif
@@ -101,10 +114,10 @@ __global__ void push_kernel(const unsigned long long* __restrict__ accum, unsign
   }
 }
 
-template <bool COUNT, bool ALL_SMEM>
+template <bool COUNT, bool ALL_SMEM, bool SSTACK = false>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
-  for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
+  stage_nodes<ALL_SMEM>(s_nodes, P.sc.nodes, P.smem_nodes);
   LeafSource ls{0u, 0u, 0u};
   if (ALL_SMEM) {  // ... and the leaves' data: [nodes][spheres 2 x float4][boxes 3 x float4][leaf refs u32]
     float4* s_sph = s_nodes + 4 * P.smem_nodes;
@@ -153,6 +166,12 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   const unsigned FULL = 0xFFFFFFFFu;
   const bool media = sc.n_media != 0;
   bool done = false;
+  // the traversal stack: local memory, or — when the launch has the room — one 32-bit entry per level in shared memory
+  typename std::conditional<SSTACK, TravStackS, TravStack>::type st;
+  if constexpr (SSTACK) {
+    st.base = opaque_u32(uint32_t(__cvta_generic_to_shared(s_nodes)) + P.stack_off) + 4u * threadIdx.x;
+    st.stride = 4u * kRenderThreads;
+  }
   for (;;) {
     if (!alive && !done) {
       const float4 B0 = lds_f4(st_a + kStB);
@@ -222,7 +241,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tt), "=f"(ss) : "r"(st_a + kStB + 8u));
       t = tt, sk = __float_as_uint(ss);
     };
-    Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, 0.001f, INF, media, key_of, aux_of, cn, alive, ls);
+    Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, 0.001f, INF, media, key_of, aux_of, cn, alive, ls, st);
     if (alive) {
       const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
       float3 beta = f3(A.x, A.y, A.z);
@@ -279,6 +298,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
 }  // namespace rtb200
 #include "rt_pool.cuh"
 #include "rt_stream.cuh"
+#include "rt_refill.cuh"
 namespace rtb200 {
 
 // ---- write_color (common/color.hpp:26-58) on the device, in double like the reference ----
@@ -998,6 +1018,11 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   if (const char* e = std::getenv("RT_B200_KERNEL")) stream = std::string(e) == "stream" ? true : (std::string(e) == "mega" || std::string(e) == "pool" ? false : stream);
   if (opts->flags & (RT_RENDER_MEGAKERNEL | RT_RENDER_POOL)) stream = false;
   if (opts->flags & RT_RENDER_STREAM) stream = true, pool = false;
+  // the in-place-refill kernel (rt_refill.cuh)
+  bool refill = kDefaultRefillKernel && !pool && !stream;
+  if (const char* e = std::getenv("RT_B200_KERNEL")) refill = std::string(e) == "refill" ? true : (std::string(e) == "mega" || std::string(e) == "pool" || std::string(e) == "stream" ? false : refill);
+  if (opts->flags & (RT_RENDER_MEGAKERNEL | RT_RENDER_POOL | RT_RENDER_STREAM)) refill = false;
+  if (opts->flags & RT_RENDER_REFILL) refill = true, pool = stream = false;
   StreamLayout SL;
   std::memset(&SL, 0, sizeof SL);
   if (stream && !stream_layout(ctx, ctx->host.bvh_depth, SL)) {
@@ -1016,6 +1041,25 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     const unsigned long long first = 0ull;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
     kern<<<grid, kStreamThreads, smem, ctx->stream>>>(P);
+    RT_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  } else if (refill) {
+    const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
+    const bool all_smem = staged + kRefillStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+    if (all_smem) {
+      P.smem_nodes = ctx->sc.n_nodes, smem = staged;
+    } else {
+      P.smem_nodes = int(std::min<size_t>(size_t(P.smem_nodes), (ctx->smem_optin - 4096 - kRefillStateBytes) / 64));
+      smem = size_t(P.smem_nodes) * 64;
+    }
+    P.state_off = unsigned((smem + 15) & ~size_t(15));
+    smem = P.state_off + kRefillStateBytes;
+    void (*kern)(RenderParams) = count ? (all_smem ? refill_kernel<true, true> : refill_kernel<true, false>)
+                                       : (all_smem ? refill_kernel<false, true> : refill_kernel<false, false>);
+    RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    unsigned long long first = 0ull;
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+    kern<<<grid, kRefillThreads, smem, ctx->stream>>>(P);
     RT_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
   } else if (pool) {
@@ -1056,8 +1100,17 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     }
     P.state_off = unsigned((smem + 15) & ~size_t(15));
     smem = P.state_off + kStateBytes;
-    void (*kern)(RenderParams) = count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
-                                       : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
+    // The traversal stacks go to shared memory too (one 32-bit entry per tree level and thread) when the child codes fit
+    // their 16 bits and shared memory then still leaves L1 at least 64 KB for the spills and the global-memory scene
+    // data: +2..3 % on bouncing_spheres / book1_final (40 KB staged), but -1.4..-7 % on book2_final, whose 127 KB staged
+    // BVH + 50 KB of stacks would leave L1 23 KB (gpurun_out/ab_ss1.log).
+    const size_t stack_bytes = size_t(std::max(1, ctx->host.bvh_depth)) * 4 * kRenderThreads;
+    const bool sstack = all_smem && RT_SMEM_STACK && ctx->sc.n_nodes <= kSmemStackMaxCode && ((ctx->sc.n_leaf_refs << 3) | 7) <= kSmemStackMaxCode &&
+                        smem + stack_bytes <= kSmemStackBudget && smem + stack_bytes + 4096 <= ctx->smem_optin;
+    if (sstack) P.stack_off = unsigned(smem), smem += stack_bytes;
+    void (*kern)(RenderParams) = sstack ? (count ? render_kernel<true, true, true> : render_kernel<false, true, true>)
+                                        : count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
+                                                : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
     RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // counters[0] = next work item: lanes take items with atomicAdd when they need one
     unsigned long long first = 0ull;

@@ -286,6 +286,31 @@ __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4&
   c1 = __float_as_int(dd.y);
 }
 
+#ifndef RT_NODE_CH
+#define RT_NODE_CH 2  // staged BVH nodes as (centre, half extent), node_step without per-axis min / max: +4..5.5 % on the BVH-heavy scenes, same accumulators (gpurun_out/ab_ch1.log, ab_ss1.log); 0 = the (lo, hi) form
+#endif
+// Copies the first `n` BVH node records into shared memory.  With RT_NODE_CH and a fully staged BVH every (lo, hi) pair
+// becomes (centre, half extent) on the way, rounded so that [c - h, c + h] contains [lo, hi]: the box the traversal sees
+// never shrinks.
+template <bool ALL_SMEM>
+__device__ __forceinline__ void stage_nodes(float4* s_nodes, const float4* __restrict__ g_nodes, int n) {
+  if (RT_NODE_CH && ALL_SMEM) {
+    auto ch = [](float& lo, float& hi) {
+      const float c = 0.5f * (lo + hi);
+      const float h = fmaxf(__fsub_ru(hi, c), __fsub_ru(c, lo));
+      lo = c, hi = h;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float4 a = g_nodes[4 * i], b = g_nodes[4 * i + 1], c = g_nodes[4 * i + 2];
+      ch(a.x, a.w), ch(a.y, b.x), ch(a.z, b.y);  // child 0: x, y, z
+      ch(b.z, c.y), ch(b.w, c.z), ch(c.x, c.w);  // child 1
+      s_nodes[4 * i] = a, s_nodes[4 * i + 1] = b, s_nodes[4 * i + 2] = c, s_nodes[4 * i + 3] = g_nodes[4 * i + 3];
+    }
+  } else {
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_nodes[i] = g_nodes[i];
+  }
+}
+
 // constant_medium::hit for one medium: entry/exit over the boundary primitives,
 // then an exponential free-flight sample.  `u` is the uniform this medium owns for this ray.
 __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium& m, float3 o, float3 d, float time, float& t1, float& t2) {
@@ -415,6 +440,7 @@ enum : int { MODE_SHADE = 0, MODE_NODE = 1, MODE_LEAF = 2, MODE_DONE = 3 };
 
 struct TravState {
   float3 o, d, inv, ood;
+  float3 ainv;  // |1/d| (RT_NODE_CH node steps only; dead otherwise)
   float time, tmin;
   Hit best;
   uint32_t skip;  // the primitive the ray starts on (REF_NONE for camera rays / medium scatters)
@@ -439,6 +465,47 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
   ts.cur = kTravDone;
   return MODE_SHADE;  // traversal finished: ts.best is the answer
 }
+__device__ __forceinline__ void trav_push(TravState& ts, TravStack& st, int node, float t) {
+  // no overflow guard: rt_upload_scene rejects a BVH deeper than kStackDepth, and the stack never holds more
+  // entries than the tree has levels
+  st.node[ts.sp] = node;
+  st.t[ts.sp] = t;
+  ts.sp++;
+}
+
+// The same stack in SHARED memory, for kernels whose launch has the room (render_range decides): one 32-bit entry per
+// level, (entry distance rounded DOWN to bf16) << 16 | 16-bit child code, laid out [level][thread] so that a warp's
+// accesses to one level hit 32 different banks.  One STS per push and one LDS per pop instead of two local-memory
+// accesses each, no L1 misses (the local stack's lines compete with the spills for what shared memory leaves of L1:
+// 71 % hit rate, profiles/r15_render_lean.md), and the rounded distance is a lower bound of the real one, so a pop
+// never culls a subtree the local stack would keep: the closest hit is the same.  Needs child codes that fit 16 bits
+// (< 32768 nodes, < 4096 leaf references) and a tree no deeper than the levels the launch reserved; ts.sp is the
+// shared-window byte address of the next free entry.
+struct TravStackS {
+  uint32_t base;    // address of this thread's level-0 entry
+  uint32_t stride;  // bytes between levels = 4 x threads per CTA
+};
+constexpr int kSmemStackMaxCode = 32767;
+__device__ __forceinline__ int trav_pop(TravState& ts, const TravStackS& st) {
+  while (uint32_t(ts.sp) != st.base) {
+    ts.sp -= int(st.stride);
+    uint32_t e;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(uint32_t(ts.sp)) : "memory");
+    if (__uint_as_float(e & 0xFFFF0000u) <= ts.best.t) {
+      ts.cur = int(e << 16) >> 16;
+      return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
+    }
+  }
+  ts.cur = kTravDone;
+  return MODE_SHADE;
+}
+__device__ __forceinline__ void trav_push(TravState& ts, TravStackS& st, int node, float t) {
+  // entry distances are >= tmin > 0: truncating the mantissa rounds down
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(uint32_t(ts.sp)), "r"((__float_as_uint(t) & 0xFFFF0000u) | (uint32_t(node) & 0xFFFFu)) : "memory");
+  ts.sp += int(st.stride);
+}
+__device__ __forceinline__ void trav_reset(TravState& ts, const TravStack&) { ts.sp = 0; }
+__device__ __forceinline__ void trav_reset(TravState& ts, const TravStackS& st) { ts.sp = int(st.base); }
 
 // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
 __device__ __forceinline__ void trav_set_ray(TravState& ts, float3 o, float3 d, float time, float tmin, uint32_t skip) {
@@ -446,6 +513,7 @@ __device__ __forceinline__ void trav_set_ray(TravState& ts, float3 o, float3 d, 
   ts.inv = f3(fabsf(d.x) > 1e-30f ? rcp_fast(d.x) : copysignf(1e30f, d.x), fabsf(d.y) > 1e-30f ? rcp_fast(d.y) : copysignf(1e30f, d.y),
               fabsf(d.z) > 1e-30f ? rcp_fast(d.z) : copysignf(1e30f, d.z));
   ts.ood = o * ts.inv;
+  ts.ainv = f3(fabsf(ts.inv.x), fabsf(ts.inv.y), fabsf(ts.inv.z));
 }
 
 // The scene-enclosing media (met by every ray — the r=5000 fog of the Book-2 final scene) are not BVH leaves:
@@ -495,32 +563,55 @@ __device__ __forceinline__ int trav_begin(TravState& ts, const DeviceScene& sc, 
   return MODE_NODE;
 }
 
-template <bool COUNT, bool ALL_SMEM = false>
-__device__ __forceinline__ int node_step(TravState& ts, TravStack& st, const NodeSource& ns, unsigned int* cn) {
+template <bool COUNT, bool ALL_SMEM = false, typename Stack = TravStack>
+__device__ __forceinline__ int node_step(TravState& ts, Stack& st, const NodeSource& ns, unsigned int* cn) {
   float4 a, b, c;
   int c0, c1;
   load_node<ALL_SMEM>(ns, ts.cur, a, b, c, c0, c1);
   if (COUNT) cn[CN_NODE]++;
   const float3 inv = ts.inv, ood = ts.ood;
-  // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
-  float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
-  float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
-  float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
-  float n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
-  float f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
-  x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
-  y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
-  z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
-  float n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
-  float f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  float n0, f0, n1, f1;
+  if (RT_NODE_CH && ALL_SMEM) {
+    // Staged nodes hold (centre, half extent) per axis in the slots of (lo, hi) — see stage_nodes(): the slab's two
+    // plane distances are tc -+ h |1/d| with tc = (c - o)/d, so near and far need no per-axis min / max.  Three FFMA
+    // per axis and child instead of two FFMA + two FMNMX: the FMA and ALU pipes each take one warp instruction per two
+    // cycles (B300_MICROARCH.md, "fma vs alu split"), and the lo/hi form puts 28 of a node step's ~50 instructions on
+    // the ALU pipe against 12 on the FMA pipe; this form issues 6 fewer instructions and splits them 18 / 16.
+#if RT_NODE_CH == 2  // |1/d| through the operand modifier of FMUL: no extra registers, four FMA-pipe operations per axis
+    float tx = fmaf(a.x, inv.x, -ood.x), ty = fmaf(a.y, inv.y, -ood.y), tz = fmaf(a.z, inv.z, -ood.z);
+    float ex = a.w * fabsf(inv.x), ey = b.x * fabsf(inv.y), ez = b.y * fabsf(inv.z);
+    n0 = fmaxf(fmaxf(tx - ex, ty - ey), fmaxf(tz - ez, ts.tmin));
+    f0 = fminf(fminf(tx + ex, ty + ey), fminf(tz + ez, ts.best.t));
+    tx = fmaf(b.z, inv.x, -ood.x), ty = fmaf(b.w, inv.y, -ood.y), tz = fmaf(c.x, inv.z, -ood.z);
+    ex = c.y * fabsf(inv.x), ey = c.z * fabsf(inv.y), ez = c.w * fabsf(inv.z);
+    n1 = fmaxf(fmaxf(tx - ex, ty - ey), fmaxf(tz - ez, ts.tmin));
+    f1 = fminf(fminf(tx + ex, ty + ey), fminf(tz + ez, ts.best.t));
+#else
+    const float3 ai = ts.ainv;
+    float tx = fmaf(a.x, inv.x, -ood.x), ty = fmaf(a.y, inv.y, -ood.y), tz = fmaf(a.z, inv.z, -ood.z);
+    n0 = fmaxf(fmaxf(fmaf(-a.w, ai.x, tx), fmaf(-b.x, ai.y, ty)), fmaxf(fmaf(-b.y, ai.z, tz), ts.tmin));
+    f0 = fminf(fminf(fmaf(a.w, ai.x, tx), fmaf(b.x, ai.y, ty)), fminf(fmaf(b.y, ai.z, tz), ts.best.t));
+    tx = fmaf(b.z, inv.x, -ood.x), ty = fmaf(b.w, inv.y, -ood.y), tz = fmaf(c.x, inv.z, -ood.z);
+    n1 = fmaxf(fmaxf(fmaf(-c.y, ai.x, tx), fmaf(-c.z, ai.y, ty)), fmaxf(fmaf(-c.w, ai.z, tz), ts.tmin));
+    f1 = fminf(fminf(fmaf(c.y, ai.x, tx), fmaf(c.z, ai.y, ty)), fminf(fmaf(c.w, ai.z, tz), ts.best.t));
+#endif
+  } else {
+    // slab test of both children (aabb.hpp:61-112), conservative: keep when tnear <= tfar
+    float x0 = fmaf(a.x, inv.x, -ood.x), x1 = fmaf(a.w, inv.x, -ood.x);
+    float y0 = fmaf(a.y, inv.y, -ood.y), y1 = fmaf(b.x, inv.y, -ood.y);
+    float z0 = fmaf(a.z, inv.z, -ood.z), z1 = fmaf(b.y, inv.z, -ood.z);
+    n0 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+    f0 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+    x0 = fmaf(b.z, inv.x, -ood.x), x1 = fmaf(c.y, inv.x, -ood.x);
+    y0 = fmaf(b.w, inv.y, -ood.y), y1 = fmaf(c.z, inv.y, -ood.y);
+    z0 = fmaf(c.x, inv.z, -ood.z), z1 = fmaf(c.w, inv.z, -ood.z);
+    n1 = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ts.tmin));
+    f1 = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), ts.best.t));
+  }
   const bool h0 = n0 <= f0, h1 = n1 <= f1;
   if (h0 && h1) {  // near child first, far child on the stack with its entry distance
     const bool first0 = n0 <= n1;
-    // no overflow guard: rt_upload_scene rejects a BVH deeper than kStackDepth, and the stack never holds more
-    // entries than the tree has levels
-    st.node[ts.sp] = first0 ? c1 : c0;
-    st.t[ts.sp] = first0 ? n1 : n0;
-    ts.sp++;
+    trav_push(ts, st, first0 ? c1 : c0, first0 ? n1 : n0);
     ts.cur = first0 ? c0 : c1;
     return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
   }
@@ -622,8 +713,8 @@ __device__ __forceinline__ void leaf_body(TravState& ts, int leaf, const DeviceS
     if (t != -1.0f) ts.best = Hit{t, ref};
   }
 }
-template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn>
-__device__ __forceinline__ int leaf_step(TravState& ts, const TravStack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
+template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn, typename Stack = TravStack>
+__device__ __forceinline__ int leaf_step(TravState& ts, const Stack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
                                          const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
   leaf_body<COUNT, CALLFREE, STAGED>(ts, ts.cur, sc, media, key_of, cn, ls);
   return trav_pop(ts, st);
@@ -745,12 +836,11 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
 // fetches the ray's Philox counter where a medium needs it — for the scene-enclosing media at the start (every ray of
 // such a scene, warp converged), and lazily for a medium leaf — and `aux_of(time, skip)` fetches the ray's time and the
 // primitive it starts on, which only the leaves (and the media) look at: the node loop carries neither.
-template <bool COUNT, bool ALL_SMEM, typename KeyFn, typename AuxFn>
+template <bool COUNT, bool ALL_SMEM, typename Stack, typename KeyFn, typename AuxFn>
 __device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const NodeSource& ns, float3 o, float3 d, float tmin, float tmax, bool media,
-                                                 KeyFn key_of, AuxFn aux_of, unsigned int* cn, bool active, const LeafSource& ls) {
+                                                 KeyFn key_of, AuxFn aux_of, unsigned int* cn, bool active, const LeafSource& ls, Stack& st) {
   const unsigned FULL = 0xFFFFFFFFu;
   TravState ts;
-  TravStack st;
   ts.best = Hit{tmax, REF_NONE};
   ts.cur = kTravDone;
   if (active) {
@@ -763,7 +853,7 @@ __device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const No
       aux_of(time, skip);
       ts.best = sample_global_media<COUNT>(sc, o, d, time, tmin, tmax, k, b, cn);
     }
-    ts.sp = 0;
+    trav_reset(ts, st);
     ts.cur = 0;
   }
   for (;;) {

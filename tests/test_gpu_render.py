@@ -220,6 +220,27 @@ def test_pool_kernel_is_bit_identical_to_the_megakernel(rtb, gpu_ctx, name, widt
     assert not gpu_ctx.download_accum().any() and gpu_ctx.stats().rays == 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["stream", "refill"])
+@pytest.mark.parametrize("name,width,spp", [("book2_final", 160, 48), ("cornell_smoke", 96, 40), ("book1_final", 200, 24), ("perlin_sphere", 120, 16)])
+def test_scheduling_variants_are_bit_identical_to_the_megakernel(rtb, gpu_ctx, kernel, name, width, spp):
+    """The streaming kernel (csrc/rt_stream.cuh: CTA-wide ray queues) and the in-place-refill kernel (csrc/rt_refill.cuh:
+    the warp leaves the traversal to shade as soon as enough lanes are finished) only change WHEN a ray is traced and
+    shaded, not what is computed for it: same accumulator bits and ray count as the megakernel, also on a sample shard."""
+    flag = {"stream": rtb.RT_RENDER_STREAM, "refill": rtb.RT_RENDER_REFILL}[kernel]
+    sc = rtb.Scene(name, rand_seed=1)
+    cam = sc.camera_copy(image_width=width, samples_per_pixel=spp)
+    gpu_ctx.upload_scene(sc.desc)
+    out = {}
+    for tag, flags in (("mega", rtb.RT_RENDER_MEGAKERNEL), ("alt", flag)):
+        gpu_ctx.render(cam, seed=13, flags=flags)
+        out[tag] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
+        gpu_ctx.render(cam, seed=13, flags=flags, sample_begin=3, sample_count=9)
+        out[tag + "_shard"] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
+    assert out["mega"][1] == out["alt"][1] and np.array_equal(out["mega"][0], out["alt"][0])
+    assert out["mega_shard"][1] == out["alt_shard"][1] and np.array_equal(out["mega_shard"][0], out["alt_shard"][0])
+
+
 def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
     """box() lists (quad.hpp:129-159) are flattened to ONE slab-test primitive.  With RT_B200_NO_BOXES the
     same lists stay six quads: the exact primary pass must agree on every pixel (ids, t, normal — the exact

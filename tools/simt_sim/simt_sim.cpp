@@ -225,6 +225,7 @@ struct Engine {
   int nodes_this_ray = 0;
 };
 static NodeSource g_ns;
+static long g_kind_n[6][2], g_kind_nodes[6][2], g_bounce_n[41];
 static std::vector<long> g_hist_nodes(512, 0);
 static long g_pushes = 0, g_pop_iters = 0, g_pops_ok = 0, g_max_sp = 0;
 static std::vector<long> g_hist_sp(40, 0);
@@ -378,6 +379,15 @@ static void run_mega(Job& J, int n_warps, int node_unroll) {
         if (w.p[l].alive) {
           g_hist_nodes[size_t(std::min(511, w.e[l].nodes_this_ray))]++;
           w.p[l].best = w.e[l].ts.best;
+          {
+            const Hit hb = w.e[l].ts.best;
+            int kind = hb.ref == REF_NONE ? 0 : 1 + int(hb.ref >> 30);
+            if (kind == 1 + int(REF_MEDIUM) && J.sc.n_global_media && int(hb.ref & 0x3FFFFFFFu) == J.sc.global_media[0]) kind = 5;
+            const float3 o = w.p[l].o;
+            const bool inside = o.x >= J.sc.bounds_lo[0] && o.x <= J.sc.bounds_hi[0] && o.y >= J.sc.bounds_lo[1] && o.y <= J.sc.bounds_hi[1] && o.z >= J.sc.bounds_lo[2] && o.z <= J.sc.bounds_hi[2];
+            g_kind_n[kind][inside]++, g_kind_nodes[kind][inside] += w.e[l].nodes_this_ray;
+            g_bounce_n[std::min(40, J.cam.max_depth - w.p[l].depth)]++;
+          }
           tags.push_back(shade_path(J, w.p[l]));
           n_dead += !w.p[l].alive;
         }
@@ -642,6 +652,85 @@ static void run_sym(Job& J, const SymOpts& O) {
          double(refill_lanes) / std::max(1L, refills), starved_polls);
 }
 
+
+// ---- policy: megakernel with IN-PLACE lane refill ---------------------------------------------------------------------
+// A lane still owns its path, but the warp leaves the traversal as soon as `shade_thr` lanes have finished their ray:
+// those lanes shade / regenerate / seed the next ray while the others keep their traversal suspended (state parked in
+// shared memory: `switch_cost` instructions per transition for the whole warp), then everybody traverses again.
+struct InplaceOpts {
+  int n_warps = 28, node_thr = 10, shade_thr = 16, node_unroll = 2;
+  double switch_cost = 40;
+};
+static void run_inplace(Job& J, const InplaceOpts& O) {
+  struct Warp {
+    Path p[32];
+    Engine e[32];
+    bool finished = false;
+  };
+  std::vector<Warp> warps(static_cast<size_t>(O.n_warps));
+  for (Warp& w : warps)
+    for (Engine& e : w.e) e.ts.cur = kTravDone;
+  int live_warps = O.n_warps;
+  long n_shade_rounds = 0, n_shade_lanes = 0;
+  while (live_warps) {
+    for (Warp& w : warps) {
+      if (w.finished) continue;
+      // ---- SHADE: every lane whose traversal is over ----
+      std::vector<ShadeTag> tags;
+      int n_dead = 0, n_regen = 0, n_fetch = 0, n_new = 0, n_lanes = 0;
+      for (int l = 0; l < 32; l++) {
+        if (w.e[l].ts.cur != kTravDone || w.p[l].done) continue;
+        n_lanes++;
+        if (w.p[l].alive) {
+          g_hist_nodes[size_t(std::min(511, w.e[l].nodes_this_ray))]++;
+          w.p[l].best = w.e[l].ts.best;
+          tags.push_back(shade_path(J, w.p[l]));
+          n_dead += !w.p[l].alive;
+        }
+        if (!w.p[l].alive) {
+          bool fetched;
+          if (regenerate(J, w.p[l], fetched)) n_regen++;
+          n_fetch += fetched;
+        }
+        if (w.p[l].alive) begin_ray(J, w.e[l], w.p[l], true), n_new++;
+      }
+      n_shade_rounds++, n_shade_lanes += n_lanes;
+      charge("switch", O.switch_cost, 32);
+      charge_shade("shade", tags);
+      charge("shade", C.deposit, n_dead);
+      charge("regen", C.regen, n_regen), charge("regen", C.item_fetch, n_fetch);
+      charge("set_ray", C.set_ray, n_new);
+      if (J.sc.n_global_media) charge("global_media", C.gm * J.sc.n_global_media, n_new);
+      std::vector<Engine*> lanes;
+      std::vector<Path*> paths;
+      int tracing = 0;
+      for (int l = 0; l < 32; l++) lanes.push_back(&w.e[l]), paths.push_back(&w.p[l]), tracing += w.e[l].ts.cur != kTravDone;
+      if (!tracing) {
+        bool all_done = true;
+        for (int l = 0; l < 32; l++) all_done = all_done && w.p[l].done;
+        if (all_done) w.finished = true, live_warps--;
+        continue;
+      }
+      // ---- TRACE until shade_thr lanes wait for a shade (or nobody is tracing) ----
+      for (;;) {
+        charge("trav_vote", C.vote, 32);
+        int want = 0, leafs = 0, waiting = 0;
+        for (int l = 0; l < 32; l++) {
+          const int c = w.e[l].ts.cur;
+          want += c >= 0, leafs += (c < 0 && c != kTravDone), waiting += (c == kTravDone && !w.p[l].done);
+        }
+        if (want + leafs == 0 || waiting >= O.shade_thr) break;
+        if (want >= O.node_thr || leafs == 0) {
+          for (int u = 0; u < O.node_unroll; u++) sim_node_step(lanes, "node");
+        } else {
+          sim_leaf_step(J, lanes, paths, "leaf");
+        }
+      }
+    }
+  }
+  printf("inplace: %ld shade rounds, %.1f lanes each\n", n_shade_rounds, double(n_shade_lanes) / n_shade_rounds);
+}
+
 int main(int argc, char** argv) {
   std::string scene = argc > 1 ? argv[1] : "book2_final", policy = argc > 2 ? argv[2] : "mega";
   std::map<std::string, double> kv;
@@ -679,6 +768,11 @@ int main(int argc, char** argv) {
          d.n_spheres, d.n_boxes, d.n_quads, d.n_media, d.n_global_media, J.cam.W, J.cam.H, J.cam.max_depth);
   if (policy == "mega") {
     run_mega(J, int(opt("warps", 28)), int(opt("unroll", 2)));
+  } else if (policy == "inplace") {
+    InplaceOpts O;
+    O.n_warps = int(opt("warps", 28)), O.node_thr = int(opt("node_thr", 10)), O.shade_thr = int(opt("shade_thr", 16)), O.node_unroll = int(opt("unroll", 2));
+    O.switch_cost = opt("switch", 40);
+    run_inplace(J, O);
   } else if (policy == "sym") {
     SymOpts O;
     O.n_slots = int(opt("slots", 1024)), O.n_warps = int(opt("warps", 24)), O.refill_thr = int(opt("refill", 8)), O.node_unroll = int(opt("unroll", 1));
@@ -699,6 +793,15 @@ int main(int argc, char** argv) {
     printf("%-14s %10.2f %10.1f %7.2f %6.1f%%\n", kvp.first.c_str(), kvp.second.W / J.rays, kvp.second.T / J.rays, kvp.second.T / kvp.second.W,
            100 * kvp.second.W / W);
   printf("%-14s %10.2f %10.1f %7.2f\n", "TOTAL", W / J.rays, T / J.rays, T / W);
+  {
+    const char* kn[6] = {"none", "sphere", "quad", "medium", "box", "gmedium"};
+    for (int k = 0; k < 6; k++)
+      for (int in = 0; in < 2; in++)
+        if (g_kind_n[k][in]) printf("hit %-8s origin %s: %6.2f%% of rays, %.2f nodes\n", kn[k], in ? "inside " : "outside", 100.0 * g_kind_n[k][in] / J.rays, double(g_kind_nodes[k][in]) / g_kind_n[k][in]);
+    printf("rays by bounce:");
+    for (int b = 0; b < 41; b++) printf(" %.3f", double(g_bounce_n[b]) / J.samples);
+    printf("\n");
+  }
   long tot = 0, acc = 0;
   for (long v : g_hist_nodes) tot += v;
   printf("node visits per ray: ");
