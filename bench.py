@@ -35,11 +35,48 @@ F_SHADE = dict(lambertian=15, metal=35, dielectric=60, light=0, isotropic=15, ch
 # bytes per unit (fp32 device layouts): BVH2 node with both child boxes 64 B, sphere 32 B, quad 48 B
 B_NODE, B_SPH, B_QUAD, B_TEXEL, B_PERLIN = 64, 32, 48, 4, 56 * 16 + 7 * 24
 B_BOXPRIM = 48
-# from the committed ncu capture profiles/r15_render_lean.md (render_kernel, book2_final 800x800 x 256 spp):
-# dram__bytes_read.sum + dram__bytes_write.sum = 33.0 MB + 1.376 GB per 163.84 M samples (traversal-stack / spill
-# write-backs; the scene itself is cache resident), issue-slot utilisation and active lanes per instruction
-NCU_DRAM_BYTES_PER_SAMPLE = (33.013504e6 + 1.375699e9) / (800 * 800 * 256)
-NCU_ISSUE_UTIL, NCU_LANES = 0.750, 9.97
+# The figures bench.py cannot measure itself (DRAM traffic, issue-slot utilisation, active lanes) come from the last ncu
+# capture as summarised by tools/ncu_summary.py into profiles/latest_ncu.json, which records the sha256 of csrc/ it was
+# taken on: when the kernels have changed since, the figures are omitted rather than pasted.
+PER_CONFIG = [  # BASELINE.json configs C1-C4 at their own size (C5 is the headline workload of the line itself)
+    ("C1", "book1_final", dict(image_width=1200, samples_per_pixel=10, max_depth=50)),
+    ("C2", "bouncing_spheres", dict(image_width=400, samples_per_pixel=100)),
+    ("C3a", "earth", dict(image_width=400, samples_per_pixel=100)),
+    ("C3b", "perlin_sphere", dict(image_width=400, samples_per_pixel=100)),
+    ("C4", "cornell_smoke", dict(image_width=600, samples_per_pixel=200, max_depth=50)),
+]
+PER_CONFIG_CPU_SPP = {"C1": 1, "C2": 8, "C3a": 8, "C3b": 8, "C4": 2}  # bounded 1-thread reference samples (2-3 s each)
+HASH_SPP = 32  # the GPU-count-invariance job: sample indices 0..31 of every pixel, seed 0
+
+
+def csrc_sha():
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "raytracing-practice_b200", "csrc", "*"))):
+        if f.endswith((".cu", ".cuh", ".h", ".hpp")):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def latest_ncu():
+    p = os.path.join(ROOT, "profiles", "latest_ncu.json")
+    if not os.path.exists(p):
+        return None, "profiles/latest_ncu.json is missing"
+    d = json.load(open(p))
+    if d.get("csrc_sha") != csrc_sha():
+        return None, f"profiles/latest_ncu.json was captured on csrc {d.get('csrc_sha')}, this build is {csrc_sha()}: omitted"
+    return d, d.get("source", "profiles/latest_ncu.json")
+
+
+def fnv1a64_words(a):
+    """FNV-1a over the 64-bit words of an int64 array (the accumulator): h = (h ^ w) * prime mod 2^64."""
+    h, prime, mask = 0xCBF29CE484222325, 0x100000001B3, (1 << 64) - 1
+    for w in a.reshape(-1).view("uint64").tolist():
+        h = ((h ^ w) * prime) & mask
+    return f"{h:016x}"
 
 
 def parse():
@@ -51,7 +88,9 @@ def parse():
     ap.add_argument("--scene", default=SCENE)
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (0 = the config's 10,000)")
     ap.add_argument("--width", type=int, default=0)
-    ap.add_argument("--cpu-spp", type=int, default=3, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample (SURVEY 8(d): >= 8)")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the C1-C4 block")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (build/dropin, the C++ camera::render)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = behind its render kernel every rank adds its accumulator into rank 0's buffer with our own "
@@ -131,7 +170,8 @@ def cpu_baseline(args):
     n = j["width"] * j["height"] * j["spp"]
     return {"value": n / j["seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
             "sample": f"{args.scene} {j['width']}x{j['height']} at {j['spp']} spp (of the config's 10,000), max_depth {j['max_depth']}; "
-                      f"unmodified reference camera::render via oracle/_ref/ref_harness (g++ -O2), 1 process x 1 thread as shipped; "
+                      f"unmodified reference camera::render via oracle/_ref/ref_harness (g++ -O2), 1 process x 1 thread as shipped, "
+                      f"timed by the harness around camera::render only (no process start / scene build); "
                       f"rotate_y/constant_medium/isotropic are oracle/ref_ext.hpp (absent from the reference)",
             "seconds": j["seconds"], "rays": j["rays"], "mrays_per_s": j["rays"] / j["seconds"] / 1e6, "host_cores_available": os.cpu_count()}
 
@@ -151,6 +191,35 @@ def oracle_port_baseline(args, threads):
             "rays": rays, "mrays_per_s": rays / dt / 1e6, "host_cores_available": os.cpu_count()}
 
 
+def dropin_leg(args, world, W, H, spp):
+    """e2e through the REAL drop-in call: a C++ scene program written like the reference's main.cpp (tests/cpp/dropin_main.cpp
+    -> build/dropin) from process start to its PPM closed: rt_init on every device, scene build + flatten, upload, render
+    sharded over the devices, on-device reduce, download, P3 text.  camera::render's own breakdown comes from RT_B200_TIMING."""
+    exe = os.path.join(ROOT, "build", "dropin")
+    if not os.path.exists(exe):
+        return {"unavailable": "build/dropin is not built (python __graft_entry__.py)"}
+    rtb = importlib.import_module("raytracing-practice_b200")
+    env = dict(os.environ, RT_B200_DEVICES=",".join(str(i) for i in range(world)), RT_B200_TIMING="1")
+    if rtb.default_image_dir():
+        env["RTW_IMAGES"] = rtb.default_image_dir()
+    out = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"rtb200_dropin_{os.getpid()}.ppm")
+    try:
+        subprocess.run([exe, "quads", out, "64", "4"], env=env, capture_output=True, timeout=120)  # page the binary in
+        t0 = time.time()
+        r = subprocess.run([exe, args.scene, out, str(W), str(spp)], env=env, capture_output=True, text=True, timeout=600)
+        wall = time.time() - t0
+        size = os.path.getsize(out) if os.path.exists(out) else 0
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+    if r.returncode != 0:
+        return {"error": r.stderr[-300:]}
+    parts = [json.loads(l[len("RTB200_TIMING "):]) for l in r.stderr.splitlines() if l.startswith("RTB200_TIMING ")]
+    return {"value": W * H * spp / wall, "unit": UNIT, "process_wall_ms": round(wall * 1e3, 1), "ppm_bytes": size, "devices": world,
+            "camera_render_ms": parts[-1] if parts else None,
+            "path": "process start -> scene build -> camera::render(std::ofstream, world) -> P3 file closed -> process exit (build/dropin, C++ host API)"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation on all host threads.  The reference
     is serial and not re-entrant (global rand()), so 'all threads' = one process per core, each
@@ -161,32 +230,45 @@ def run_reference_arm(args):
     rtb = importlib.import_module("raytracing-practice_b200")
     cores = os.cpu_count() or 1
     have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_harness"))
-    spp_each = max(1, args.cpu_spp // 3)
+    # Timed steps render `spp_each` spp per process: 8 when K timed steps of it fit ~4 minutes, else as many
+    # as fit (>= 2); the untimed warm-up steps render 1 spp.  A step's time is the harness's own clock around
+    # camera::render (max over the concurrent processes): no process start, scene build or JPEG decode in it.
+    sec_per_spp = 2.4  # one process, one spp of this workload with all cores busy (measured by the first warm-up below)
     times, last = [], None
+    spp_each = 8
     for step in range(args.warmup + args.steps):
+        timed = step >= args.warmup
+        if step == args.warmup:
+            spp_each = int(max(2, min(8, 240.0 / max(1, args.steps) / max(sec_per_spp, 1e-3))))
+        spp_now = spp_each if timed else 1
         t0 = time.time()
         if have_ref:
-            procs = [cpu_reference_once(args.scene, args.width, spp_each, seed=100 * step + c + 1) for c in range(cores)]
+            procs = [cpu_reference_once(args.scene, args.width, spp_now, seed=100 * step + c + 1) for c in range(cores)]
             res = [parse_harness(p) for p in procs]
             samples = sum(r["width"] * r["height"] * r["spp"] for r in res)
             rays = sum(r["rays"] for r in res)
             dims = (res[0]["width"], res[0]["height"], res[0]["max_depth"])
+            dt = max(r["seconds"] for r in res)
         else:
             from oracle import orc
 
             sc = rtb.Scene(args.scene, rand_seed=1)
             cam = sc.camera_copy(**({"image_width": args.width} if args.width else {}))
-            _, _, rays = orc.render_linear(sc.desc, cam, spp=spp_each * cores, seed=step + 1, threads=cores, want_sq=False, rng="glibc")
-            samples = cam.image_width * rtb.image_height(cam) * spp_each * cores
+            t1 = time.time()
+            _, _, rays = orc.render_linear(sc.desc, cam, spp=spp_now * cores, seed=step + 1, threads=cores, want_sq=False, rng="glibc")
+            dt = time.time() - t1
+            samples = cam.image_width * rtb.image_height(cam) * spp_now * cores
             dims = (cam.image_width, rtb.image_height(cam), cam.max_depth)
-        dt = time.time() - t0
-        if step >= args.warmup:
+        if not timed:
+            sec_per_spp = dt / spp_now
+        if timed:
             times.append(dt)
             last = (samples, rays)
     sec = sum(times) / len(times)
     value = last[0] / sec
-    sample = (f"{args.scene} {dims[0]}x{dims[1]}, max_depth {dims[2]}: {cores} processes x {spp_each} spp per step "
-              f"({'oracle/_ref/ref_harness = unmodified reference camera::render' if have_ref else 'oracle port'}), one per host core")
+    sample = (f"{args.scene} {dims[0]}x{dims[1]}, max_depth {dims[2]}: {cores} processes x {spp_each} spp per timed step "
+              f"({'oracle/_ref/ref_harness = unmodified reference camera::render' if have_ref else 'oracle port'}), one per host core; "
+              f"step time = the slowest process's own clock around camera::render (render only)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.scene} 800x800 x 10000 spp, max_depth 40 (BASELINE config 5); each CPU step is a bounded sample of it"},
@@ -227,6 +309,9 @@ def main():
     rtb = importlib.import_module("raytracing-practice_b200")
     dist = importlib.import_module("raytracing-practice_b200.dist")
     rank, local_rank, world = dist.init_process_group()
+    done_flag = f"/tmp/rtb200_bench_{os.environ.get('MASTER_PORT', '0')}.done"
+    if rank == 0 and os.path.exists(done_flag):
+        os.remove(done_flag)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
@@ -299,7 +384,7 @@ def main():
     launches = ctx.stats().kernel_launches - launches0
 
     # ---- e2e: the reference-facing C-ABI call sequence with host buffers ---------------------
-    e2e_steps = min(args.steps, 2)
+    e2e_steps = args.steps
     scene_bytes = sum(getattr(sc.desc.contents, n) * C.sizeof(t) for n, t in
                       [("n_hittables", rtb.rt_hittable), ("n_materials", rtb.rt_material), ("n_textures", rtb.rt_texture), ("n_perlins", rtb.rt_perlin)])
     scene_bytes += 4 * sc.desc.contents.n_child_index
@@ -353,6 +438,65 @@ def main():
                   + B_PERLIN * per_ray["noise"])
         census = dict(per_ray=per_ray, flops_per_ray=flops, bytes_per_ray=nbytes, rays_per_sample=st.rays / max(st.samples, 1))
 
+    # ---- GPU-count invariance: a fixed job (seed 0, sample indices 0..HASH_SPP-1), sharded over the ranks and reduced
+    # exactly like a timed step; the FNV-1a of rank 0's int64 accumulator must be the same string in every line --------
+    hcam = sc.camera_copy(**dict(over, samples_per_pixel=HASH_SPP))
+    if peer is not None:
+        peer.render(0, cam=hcam)
+    else:
+        hb, hc = dist.shard_samples(HASH_SPP, rank, world)
+        ctx.render(hcam, seed=0, sample_begin=hb, sample_count=hc, clear=True)
+        ctx.synchronize()
+        if world > 1:
+            dist.reduce_accum_to_rank0(ctx.accum_tensor())
+            torch.cuda.synchronize()
+    accum_fnv = fnv1a64_words(ctx.download_accum()) if rank == 0 else None
+    barrier()
+
+    # ---- the other BASELINE configurations at their own size: sample-sharded over the ranks like the headline job,
+    # rendered back to back until the device time exceeds 50 ms (they take 0.3 - 40 ms each) ------------------------
+    per_config = []
+    if not args.no_per_config:
+        for tag, scene_name, cover in PER_CONFIG:
+            psc = rtb.Scene(scene_name, rand_seed=1)
+            pcam = psc.camera_copy(**cover)
+            ctx.upload_scene(psc.desc)
+            pb, pc = dist.shard_samples(pcam.samples_per_pixel, rank, world)
+            ms_sum, reps, prays = 0.0, 0, 0
+            if pc > 0:
+                ctx.render(pcam, seed=77, sample_begin=pb, sample_count=pc, clear=True)  # warm-up (module load, clocks)
+                ctx.synchronize()
+            barrier()
+            n_reps = 3
+            while True:
+                ms_round, rays_round = 0.0, 0
+                for r_ in range(n_reps):
+                    if pc > 0:
+                        ctx.render(pcam, seed=r_, sample_begin=pb, sample_count=pc, clear=True)
+                        st_ = ctx.stats()
+                        ms_round += st_.last_render_ms
+                        rays_round += st_.rays
+                t_ = torch.tensor([ms_round, float(rays_round)], dtype=torch.float64, device=f"cuda:{local_rank}")
+                if world > 1:
+                    mx_ = t_.clone()
+                    torch.distributed.all_reduce(mx_, op=torch.distributed.ReduceOp.MAX)
+                    sm_ = t_.clone()
+                    torch.distributed.all_reduce(sm_, op=torch.distributed.ReduceOp.SUM)
+                    ms_round, rays_round = mx_[0].item(), sm_[1].item()
+                if ms_round >= 50.0 or n_reps >= 4096:
+                    ms_sum, reps, prays = ms_round, n_reps, rays_round
+                    break
+                n_reps = int(min(4096, max(n_reps * 2, n_reps * 60.0 / max(ms_round, 1e-3))))
+            pw, ph = pcam.image_width, rtb.image_height(pcam)
+            samples = pw * ph * pcam.samples_per_pixel * reps
+            per_config.append({"config": tag, "scene": scene_name, "width": pw, "height": ph, "spp": pcam.samples_per_pixel, "max_depth": pcam.max_depth,
+                               "renders": reps, "device_ms_total": round(ms_sum, 3), "ms_per_render": round(ms_sum / reps, 4),
+                               "value": samples / (ms_sum * 1e-3), "unit": UNIT, "mrays_per_s": prays / (ms_sum * 1e-3) / 1e6,
+                               "timing": "sum of the CUDA-event times of `renders` back-to-back rt_render calls of this rank's sample shard, max over ranks "
+                                         "(render only: the 15 MB exchange step is in the headline line)"})
+            psc.close()
+        ctx.upload_scene(sc.desc)
+
     # ---- max over ranks -------------------------------------------------------------------------
     vals = torch.tensor([dev_ms, wall * 1e3, e2e_sec * 1e3, float(rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -364,7 +508,12 @@ def main():
     else:
         wall_ms, e2e_ms = wall * 1e3, e2e_sec * 1e3
     if rank != 0:
+        # rank 0 now runs the drop-in leg on ALL devices: wait for it on the host (a NCCL barrier would spin on this GPU)
         ctx.close()
+        t_wait = time.time()
+        while not os.path.exists(done_flag) and time.time() - t_wait < 900:
+            time.sleep(0.05)
+        torch.distributed.destroy_process_group()
         return 0
 
     ms_per_step = dev_ms / args.steps
@@ -376,16 +525,19 @@ def main():
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp32_peak_tflops = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     kernel_rays_s = rays_per_step / world / (ms_per_step * 1e-3)  # one launch = one rank's kernel
+    ncu, ncu_src = latest_ncu()
     roofline = {"bound": "fp32",
                 "bound_note": "FP32/ALU issue under divergence - neither hbm nor tensor: the whole scene is shared-memory / L1 resident and the algorithm "
                               "has no dense contraction (SURVEY.md 8(d)); the hbm view of the same launch is in roofline.hbm",
                 "achieved": kernel_rays_s * census["flops_per_ray"] / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                 "frac": kernel_rays_s * census["flops_per_ray"] / 1e12 / fp32_peak_tflops,
-                "traffic": NCU_DRAM_BYTES_PER_SAMPLE * W * H * count,
-                "traffic_note": "DRAM bytes per launch = ncu dram__bytes_read+write per sample (profiles/r15_render_lean.md) x this launch's samples; "
-                                "stack/spill write-backs, not scene data (algorithmic bytes are served by shared memory / L1)",
-                "simt": {"issue_slot_utilisation": NCU_ISSUE_UTIL, "active_lanes_per_instruction": NCU_LANES,
-                         "lane_issue_frac": NCU_ISSUE_UTIL * NCU_LANES / 32, "source": "profiles/r15_render_lean.md (ncu --set full)"},
+                "traffic": ncu["dram_bytes_per_sample"] * W * H * count if ncu else None,
+                "traffic_note": (f"DRAM bytes per launch = ncu dram__bytes_read+write per sample ({ncu_src}) x this launch's samples; stack/spill write-backs "
+                                 "and accumulator adds, not scene data (algorithmic bytes are served by shared memory / L1)") if ncu else ncu_src,
+                "simt": ({"issue_slot_utilisation": ncu["issue_slot_utilisation"], "active_lanes_per_instruction": ncu["active_lanes_per_instruction"],
+                          "lane_issue_frac": ncu["issue_slot_utilisation"] * ncu["active_lanes_per_instruction"] / 32,
+                          "alu_pipe_utilisation": ncu.get("alu_pipe_utilisation"), "fma_pipe_utilisation": ncu.get("fma_pipe_utilisation"),
+                          "source": ncu_src} if ncu else None),
                 "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal max clock)",
                 "flops_per_ray": census["flops_per_ray"], "bytes_per_ray": census["bytes_per_ray"], "census_per_ray": census["per_ray"],
                 "hbm": {"bound": "hbm", "achieved": kernel_rays_s * census["bytes_per_ray"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -404,16 +556,33 @@ def main():
             "e2e": {"value": total_samples / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(W * H * 3),
                     "steps": e2e_steps, "path": "rt_upload_scene + rt_render + reduce + rt_download(RGB8) with host buffers, wall clock",
                     "rank0_ms": dict(zip(("upload", "render", "reduce", "download"), (round(1e3 * x, 2) for x in e2e_parts)))},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "accum_fnv": {"value": accum_fnv, "job": f"{args.scene} {W}x{H}, seed 0, sample indices 0..{HASH_SPP - 1}, sharded over {world} rank(s) and reduced like a timed "
+                                                     f"step; FNV-1a over the 64-bit words of rank 0's int64 accumulator — equal across n_gpus = the image does not depend on the GPU count"},
+            "per_config": per_config, "csrc_sha": csrc_sha()}
     if not args.no_cpu_baseline and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(args)
             line["speedup_vs_cpu_baseline_1core"] = line["e2e"]["value"] / line["cpu_baseline"]["value"]
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
+        # the same 1-thread reference figure for C1-C4 (bounded samples, run concurrently: 5 of the box's cores)
+        if per_config and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_harness")):
+            procs = [(pc_, cpu_reference_once(pc_["scene"], pc_["width"], PER_CONFIG_CPU_SPP[pc_["config"]], seed=1)) for pc_ in per_config]
+            for pc_, pr in procs:
+                try:
+                    j = parse_harness(pr)
+                    pc_["cpu_baseline"] = {"value": j["width"] * j["height"] * j["spp"] / j["seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
+                                           "sample": f"{j['spp']} spp of {pc_['spp']}, max_depth {j['max_depth']}, harness clock around camera::render"}
+                    pc_["speedup_vs_cpu_baseline_1core"] = pc_["value"] / pc_["cpu_baseline"]["value"]
+                except Exception as e:  # noqa: BLE001
+                    pc_["cpu_baseline"] = {"error": str(e)}
+    if not args.no_dropin:
+        line["e2e_dropin"] = dropin_leg(args, world, W, H, spp)
     emit(line)
     ctx.close()
     if world > 1:
+        open(done_flag, "w").close()
         torch.distributed.destroy_process_group()
     return 0
 

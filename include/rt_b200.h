@@ -298,7 +298,12 @@ enum {
   RT_TRACE_EXACT = 1, /* fp32 conservative traversal; every candidate re-evaluated in
                          fp64 with the reference's operation order (no FMA) so that the
                          winner is the one hittable::hit would report                  */
-  RT_TRACE_SKIP_MEDIA = 2 /* constant_medium is transparent          */
+  RT_TRACE_SKIP_MEDIA = 2, /* constant_medium is transparent         */
+  RT_TRACE_RENDER_KERNEL = 4 /* rt_primary_visibility only: the rays are generated and traced by the
+                         render kernel ITSELF (its AOV instantiation, planned for the scene as
+                         rt_render plans it: same staging, node form, leaf steps and stack) in
+                         fp32, media transparent — the traversal rt_render runs, under the
+                         id / t / normal gate (camera.hpp:192, hittable_list.hpp:40-64)   */
 };
 
 /* n rays given as double origin[3n], direction[3n], time[n]; interval (tmin, tmax) as
@@ -310,7 +315,9 @@ int rt_trace_rays(rt_ctx* ctx, int64_t n, const double* origin, const double* di
                   int32_t* prim_id, double* t, double* normal, uint8_t* front_face);
 
 /* Pixel-centre primary rays (no jitter, no defocus, time 0, interval (0.001, inf)),
- * generated on the device from the camera frame: SURVEY.md §8(c) convention.          */
+ * generated on the device from the camera frame: SURVEY.md §8(c) convention.  With
+ * RT_TRACE_RENDER_KERNEL the rays are the fp32 rays the render kernel builds (get_ray
+ * at zero jitter) and t / normal are its fp32 results widened to double.               */
 int rt_primary_visibility(rt_ctx* ctx, const rt_camera_desc* cam, int32_t flags,
                           int32_t* prim_id, double* t, double* normal);
 

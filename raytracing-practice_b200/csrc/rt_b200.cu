@@ -61,6 +61,10 @@ struct RenderParams {
   int smem_nodes;
   unsigned int state_off;  // byte offset of the per-thread shade-state records in dynamic shared memory
   unsigned int stack_off;  // byte offset of the shared-memory traversal stacks (kernels instantiated with SSTACK)
+  unsigned int stack_levels;  // levels reserved per thread at stack_off (checks builds test against it)
+  int* aov_id;             // render_kernel<.., AOV>: primitive id, t and shading normal of every pixel-centre ray
+  float* aov_t;
+  float* aov_n;
   float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
   StreamLayout sl;   // streaming kernel only
 };
@@ -114,7 +118,12 @@ __global__ void push_kernel(const unsigned long long* __restrict__ accum, unsign
   }
 }
 
-template <bool COUNT, bool ALL_SMEM, bool SSTACK = false>
+// AOV = true is the parity instantiation (rt_primary_visibility with RT_TRACE_RENDER_KERNEL): the SAME kernel — staging,
+// work distribution, camera ray arithmetic, closest_hit_keyfn with the same node / leaf steps and stack — traces the
+// jitter-free pixel-centre ray of every pixel (no defocus, time 0, media transparent) and, instead of shading, writes
+// the primitive id, t and normal it found, so that the traversal rt_render runs is itself under the id / t / normal gate
+// (camera.hpp:192, hittable_list.hpp:40-64).
+template <bool COUNT, bool ALL_SMEM, bool SSTACK = false, bool AOV = false>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
   stage_nodes<ALL_SMEM>(s_nodes, P.sc.nodes, P.smem_nodes);
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
     ls.refs = opaque_u32(uint32_t(__cvta_generic_to_shared(s_ref)));
   }
   __syncthreads();
-  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
+  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes, P.sc.n_nodes);
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
 
@@ -164,13 +173,16 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
   //  resumable traversal that breaks out to shade/refill finished lanes once < 8..24 lanes still traverse.
   //  Shading a half-empty warp twice costs more than the shallow traversal saves.)
   const unsigned FULL = 0xFFFFFFFFu;
-  const bool media = sc.n_media != 0;
+  const bool media = !AOV && sc.n_media != 0;
   bool done = false;
   // the traversal stack: local memory, or — when the launch has the room — one 32-bit entry per level in shared memory
   typename std::conditional<SSTACK, TravStackS, TravStack>::type st;
   if constexpr (SSTACK) {
     st.base = opaque_u32(uint32_t(__cvta_generic_to_shared(s_nodes)) + P.stack_off) + 4u * threadIdx.x;
     st.stride = 4u * kRenderThreads;
+#if RT_CHECKS
+    st.levels = P.stack_levels;
+#endif
   }
   for (;;) {
     if (!alive && !done) {
@@ -206,10 +218,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         const int py = pixel / P.cam.W, px = pixel - py * P.cam.W;
         uint4 r0 = rng_block(key, 0u, 0u);
         float ox = u01(r0.x) - 0.5f, oy = u01(r0.y) - 0.5f;
-        const float time = u01(r0.z);
+        float time = u01(r0.z);
+        if (AOV) ox = oy = time = 0.0f;
         float3 dir = fma3(float(px) + ox, P.cam.du, fma3(float(py) + oy, P.cam.dv, P.cam.p00c));
         o = P.cam.center;
-        if (P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
+        if (!AOV && P.cam.defocus) {  // uniform disk: r = sqrt(u), phi = 2 pi v (== rejection sampling in law)
           uint4 r1 = rng_block(key, 0u, 1u);
           float rr = sqrtf(u01(r1.x)), sn, cs;
           sincos_2pi(u01(r1.y), sn, cs);
@@ -242,6 +255,29 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
       t = tt, sk = __float_as_uint(ss);
     };
     Hit h = closest_hit_keyfn<COUNT, ALL_SMEM>(sc, ns, o, d, 0.001f, INF, media, key_of, aux_of, cn, alive, ls, st);
+    if (AOV) {
+      if (alive) {
+        const int pixel = __float_as_int(lds_f4(st_a + kStB).x);
+        int pid = -1;
+        float t = INF;
+        float3 n = f3(0.0f, 0.0f, 0.0f);
+        if (h.ref != REF_NONE) {
+          const Surface sf = surface_at(sc, h, o, d, 0.0f);
+          const uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
+          if (type == REF_BOX) {  // the reference quad behind this face of the box (scene_build.hpp, box_meta)
+            const int4 meta = sc.box_meta[idx >> 3];
+            pid = sc.xquads[meta.y + int((uint32_t(meta.z) >> (4u * (idx & 7u))) & 7u)].pid;
+          } else {
+            pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
+          }
+          t = h.t, n = sf.n;
+        }
+        P.aov_id[pixel] = pid, P.aov_t[pixel] = t;
+        P.aov_n[3 * pixel] = n.x, P.aov_n[3 * pixel + 1] = n.y, P.aov_n[3 * pixel + 2] = n.z;
+        alive = false;
+      }
+      continue;
+    }
     if (alive) {
       const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
       float3 beta = f3(A.x, A.y, A.z);
@@ -279,6 +315,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         // the finished sample, quantised to 2^-32, straight into the int64 accumulator (red.add.u64:
         // fire-and-forget, ~3 per 5 rays).  Integer adds commute, so the image does not depend on
         // which lane / CTA / launch / GPU contributed which sample.
+        RT_CHECK(pixel >= 0 && (unsigned long long)pixel * 3ull + 2ull < P.n_values, CHK_PIXEL);
         unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
         const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
         if (fr) atomicAdd(dst + 0, (unsigned long long)fr);
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
   extern __shared__ float4 s_nodes[];
   for (int i = threadIdx.x; i < 4 * P.smem_nodes; i += blockDim.x) s_nodes[i] = P.sc.nodes[i];
   __syncthreads();
-  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
+  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes, P.sc.n_nodes);
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
   const DeviceScene& sc = P.sc;
@@ -866,6 +903,41 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   return RT_OK;
 }
 
+// The megakernel's shared-memory plan for the uploaded scene: what is staged, where the per-thread records and the
+// traversal stacks go.  Fills P.smem_nodes / P.state_off / P.stack_off.
+struct MegaPlan {
+  size_t smem;
+  bool all_smem, sstack;
+};
+static MegaPlan plan_megakernel(const rt_ctx* ctx, RenderParams& P) {
+  // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared
+  // memory" (all BASELINE scenes): its node step then has neither the bounds test nor the global-memory path, and a
+  // leaf visit makes no global load
+  const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
+  constexpr size_t kStateBytes = size_t(32) * kRenderThreads;  // per-thread shade state (render_kernel)
+  MegaPlan mp;
+  mp.all_smem = staged + kStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+  size_t smem;
+  if (mp.all_smem) {
+    P.smem_nodes = ctx->sc.n_nodes, smem = staged;
+  } else {  // the top of the BVH only, as much as fits beside the state records
+    P.smem_nodes = int(std::min<size_t>(size_t(ctx->smem_nodes), (ctx->smem_optin - 4096 - kStateBytes) / 64));
+    smem = size_t(P.smem_nodes) * 64;
+  }
+  P.state_off = unsigned((smem + 15) & ~size_t(15));
+  smem = P.state_off + kStateBytes;
+  // The traversal stacks go to shared memory too (one 32-bit entry per tree level and thread) when the child codes fit
+  // their 16 bits and shared memory then still leaves L1 at least 64 KB for the spills and the global-memory scene
+  // data: +2..3 % on bouncing_spheres / book1_final (40 KB staged), but -1.4..-7 % on book2_final, whose 127 KB staged
+  // BVH + 50 KB of stacks would leave L1 23 KB (gpurun_out/ab_ss1.log).
+  const size_t stack_bytes = size_t(std::max(1, ctx->host.bvh_depth)) * 4 * kRenderThreads;
+  mp.sstack = mp.all_smem && RT_SMEM_STACK && ctx->sc.n_nodes <= kSmemStackMaxCode && ((ctx->sc.n_leaf_refs << 3) | 7) <= kSmemStackMaxCode &&
+              smem + stack_bytes <= kSmemStackBudget && smem + stack_bytes + 4096 <= ctx->smem_optin;
+  if (mp.sstack) P.stack_off = unsigned(smem), P.stack_levels = unsigned(std::max(1, ctx->host.bvh_depth)), smem += stack_bytes;
+  mp.smem = smem;
+  return mp;
+}
+
 static cudaError_t launch_render(void (*kern)(RenderParams), int grid, size_t smem, cudaStream_t stream, RenderParams& P) {
   kern<<<grid, kRenderThreads, smem, stream>>>(P);
   return cudaGetLastError();
@@ -1089,28 +1161,11 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared
     // memory" (all BASELINE scenes): its node step then has neither the bounds test nor the global-memory path, and a
     // leaf visit makes no global load
-    const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
-    constexpr size_t kStateBytes = size_t(32) * kRenderThreads;  // per-thread shade state (render_kernel)
-    const bool all_smem = staged + kStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
-    if (all_smem) {
-      P.smem_nodes = ctx->sc.n_nodes, smem = staged;
-    } else {  // the top of the BVH only, as much as fits beside the state records
-      P.smem_nodes = int(std::min<size_t>(size_t(P.smem_nodes), (ctx->smem_optin - 4096 - kStateBytes) / 64));
-      smem = size_t(P.smem_nodes) * 64;
-    }
-    P.state_off = unsigned((smem + 15) & ~size_t(15));
-    smem = P.state_off + kStateBytes;
-    // The traversal stacks go to shared memory too (one 32-bit entry per tree level and thread) when the child codes fit
-    // their 16 bits and shared memory then still leaves L1 at least 64 KB for the spills and the global-memory scene
-    // data: +2..3 % on bouncing_spheres / book1_final (40 KB staged), but -1.4..-7 % on book2_final, whose 127 KB staged
-    // BVH + 50 KB of stacks would leave L1 23 KB (gpurun_out/ab_ss1.log).
-    const size_t stack_bytes = size_t(std::max(1, ctx->host.bvh_depth)) * 4 * kRenderThreads;
-    const bool sstack = all_smem && RT_SMEM_STACK && ctx->sc.n_nodes <= kSmemStackMaxCode && ((ctx->sc.n_leaf_refs << 3) | 7) <= kSmemStackMaxCode &&
-                        smem + stack_bytes <= kSmemStackBudget && smem + stack_bytes + 4096 <= ctx->smem_optin;
-    if (sstack) P.stack_off = unsigned(smem), smem += stack_bytes;
-    void (*kern)(RenderParams) = sstack ? (count ? render_kernel<true, true, true> : render_kernel<false, true, true>)
-                                        : count ? (all_smem ? render_kernel<true, true> : render_kernel<true, false>)
-                                                : (all_smem ? render_kernel<false, true> : render_kernel<false, false>);
+    const MegaPlan mp = plan_megakernel(ctx, P);
+    smem = mp.smem;
+    void (*kern)(RenderParams) = mp.sstack ? (count ? render_kernel<true, true, true> : render_kernel<false, true, true>)
+                                           : count ? (mp.all_smem ? render_kernel<true, true> : render_kernel<true, false>)
+                                                   : (mp.all_smem ? render_kernel<false, true> : render_kernel<false, false>);
     RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // counters[0] = next work item: lanes take items with atomicAdd when they need one
     unsigned long long first = 0ull;
@@ -1137,6 +1192,18 @@ int rt_synchronize(rt_ctx* ctx) {
   DebugScope dbg("rt_synchronize");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#if RT_CHECKS
+  {  // checks build: a failed device-side bounds check turns into an error here
+    unsigned int bad = 0, zero = 0, count = 0;
+    RT_CUDA(ctx, cudaMemcpyFromSymbol(&bad, g_rt_check_fail, sizeof bad));
+    RT_CUDA(ctx, cudaMemcpyFromSymbol(&count, g_rt_check_count, sizeof count));
+    if (std::getenv("RT_B200_DEBUG")) std::fprintf(stderr, "[rt_b200 checks] %u device-side checks evaluated (mod 2^32), worst failing site %u\n", count, bad);
+    if (bad) {
+      RT_CUDA(ctx, cudaMemcpyToSymbol(g_rt_check_fail, &zero, sizeof zero));
+      return fail(ctx, RT_ERR_CUDA, "device-side bounds check failed at site " + std::to_string(bad) + " (rt_device.cuh, CHK_*)");
+    }
+  }
+#endif
   return RT_OK;
 }
 
@@ -1341,6 +1408,42 @@ int rt_primary_visibility(rt_ctx* ctx, const rt_camera_desc* cam, int32_t flags,
   rt_camera_initialize(cam, &f);
   const long long n = (long long)f.image_width * f.image_height;
   Scratch sx;
+  if (flags & RT_TRACE_RENDER_KERNEL) {
+    // the pixel-centre rays go through render_kernel itself (its AOV instantiation), planned exactly as rt_render plans
+    // it for this scene: same staging, same node form, same stack
+    if (flags & RT_TRACE_EXACT) return fail(ctx, RT_ERR_INVALID, "RT_TRACE_RENDER_KERNEL is the fp32 production traversal: not with RT_TRACE_EXACT");
+    RenderParams P;
+    std::memset(&P, 0, sizeof P);
+    P.sc = ctx->sc;
+    fill_camera(cam, f, P.cam);
+    P.cam.max_depth = 1;
+    P.sample_begin = 0, P.sample_count = 1, P.chunk = 1, P.n_chunks = 1;
+    P.tiles_x = (f.image_width + 7) / 8, P.tiles_y = (f.image_height + 3) / 4;
+    const unsigned long long n_items = (unsigned long long)P.tiles_x * P.tiles_y * 32ull;
+    if (n_items >= 0xFFFFFFFFull - (unsigned long long)ctx->sm_count * kRenderThreads) return fail(ctx, RT_ERR_INVALID, "image too large");
+    P.per_chunk = unsigned(n_items), P.n_items = unsigned(n_items);
+    P.counters = sx.alloc<unsigned long long>(32);
+    P.aov_id = sx.alloc<int>(size_t(n));
+    P.aov_t = sx.alloc<float>(size_t(n));
+    P.aov_n = sx.alloc<float>(size_t(3 * n));
+    if (!P.counters || !P.aov_id || !P.aov_t || !P.aov_n) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");
+    RT_CUDA(ctx, cudaMemsetAsync(P.counters, 0, 32 * sizeof(unsigned long long), ctx->stream));
+    const MegaPlan mp = plan_megakernel(ctx, P);
+    void (*kern)(RenderParams) = mp.sstack ? render_kernel<false, true, true, true> : (mp.all_smem ? render_kernel<false, true, false, true> : render_kernel<false, false, false, true>);
+    RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mp.smem)));
+    RT_CUDA(ctx, launch_render(kern, ctx->sm_count, mp.smem, ctx->stream, P));
+    ctx->launches++;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float> ht(static_cast<size_t>(n)), hn(static_cast<size_t>(3 * n));
+    if (prim_id) RT_CUDA(ctx, cudaMemcpy(prim_id, P.aov_id, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    RT_CUDA(ctx, cudaMemcpy(ht.data(), P.aov_t, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    RT_CUDA(ctx, cudaMemcpy(hn.data(), P.aov_n, size_t(3 * n) * 4, cudaMemcpyDeviceToHost));
+    if (t)
+      for (long long i = 0; i < n; i++) t[i] = double(ht[size_t(i)]);
+    if (normal)
+      for (long long i = 0; i < 3 * n; i++) normal[i] = double(hn[size_t(i)]);
+    return RT_OK;
+  }
   double* d_o = sx.alloc<double>(size_t(3 * n));
   double* d_d = sx.alloc<double>(size_t(3 * n));
   if (!d_o || !d_d) return fail(ctx, RT_ERR_CUDA, "cudaMalloc failed");

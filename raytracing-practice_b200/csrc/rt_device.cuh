@@ -18,6 +18,32 @@
 
 namespace rtb200 {
 
+// ---- checks build (-DRT_CHECKS=1; tools/sanitize.sh) ---------------------------------------------------------------------
+// compute-sanitizer is closed on this GPU pool, so the library carries its own bounds checks: in a checks build every
+// dynamically indexed access of the kernels (BVH nodes, leaf references, primitive / material / texture / texel arrays,
+// both traversal stacks, the accumulator) is tested against its array's size; a failure records its site code in
+// g_rt_check_fail (largest code wins) and the access is clamped, and the next rt_synchronize / rt_get_stats returns
+// RT_ERR_CUDA naming the site.  Product builds compile none of it.
+#ifndef RT_CHECKS
+#define RT_CHECKS 0
+#endif
+#if RT_CHECKS
+__device__ unsigned int g_rt_check_fail = 0u;
+__device__ unsigned int g_rt_check_count = 0u;  // checks evaluated (a checks build that evaluates none proves nothing)
+#define RT_CHECK(cond, code) \
+  do { \
+    atomicAdd(&g_rt_check_count, 1u); \
+    if (!(cond)) atomicMax(&g_rt_check_fail, (unsigned int)(code)); \
+  } while (0)
+#else
+#define RT_CHECK(cond, code) \
+  do { \
+  } while (0)
+#endif
+// site codes
+enum : int { CHK_NODE = 1, CHK_STACK_LOCAL = 2, CHK_STACK_SMEM = 3, CHK_LEAF_REF = 4, CHK_SPHERE = 5, CHK_QUAD = 6, CHK_BOX = 7, CHK_MEDIUM = 8, CHK_MATERIAL = 9,
+             CHK_TEXTURE = 10, CHK_TEXEL = 11, CHK_PIXEL = 12, CHK_BREF = 13, CHK_STATE = 14 };
+
 // Big, rarely executed helpers are kept OUT of line (RT_OUTLINE): the fully inlined megakernel was
 // 4,096 SASS instructions = 64 KB, and with 32 resident warps at scattered PCs the top stall was
 // 'no instruction' (instruction-cache misses), profiles/r04_render_t1024.md.
@@ -240,13 +266,20 @@ struct NodeSource {
   const float4* gmem;
   int smem_nodes;
   uint32_t smem_addr;  // 32-bit shared-window address of `smem`, see node_source()
+#if RT_CHECKS
+  int n_nodes;
+#endif
 };
 // The shared address is laundered through an opaque mov so that it LIVES IN A REGISTER: left to itself the compiler
 // rebuilds it (S2R CgaCtaId, MOV, LEA, IMAD) at every node step.
-__device__ __forceinline__ NodeSource node_source(const float4* smem, const float4* gmem, int smem_nodes) {
+__device__ __forceinline__ NodeSource node_source(const float4* smem, const float4* gmem, int smem_nodes, int n_nodes = 0x7fffffff) {
   uint32_t a = uint32_t(__cvta_generic_to_shared(smem));
   asm volatile("mov.u32 %0, %0;" : "+r"(a));
+#if RT_CHECKS
+  return NodeSource{smem, gmem, smem_nodes, a, n_nodes};
+#else
   return NodeSource{smem, gmem, smem_nodes, a};
+#endif
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
@@ -272,6 +305,7 @@ __device__ __forceinline__ uint32_t opaque_u32(uint32_t a) {  // keeps a shared 
 template <bool ALL_SMEM = false>
 __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
   float4 dd;
+  RT_CHECK(idx >= 0 && idx < ns.n_nodes, CHK_NODE);
   if (ALL_SMEM || idx < ns.smem_nodes) {
     // 32-bit shared-window address: through the generic pointer the compiler rebuilt the window base
     // (S2R CgaCtaId, MOV, LEA, LEA) at every node step
@@ -317,6 +351,7 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
   const float INF = __int_as_float(0x7f800000);
   if (m.n_bref == 1) {  // a single sphere (the usual boundary): both passes below come from ONE pair of roots
     const uint32_t ref = __ldg(sc.medium_brefs + m.first_bref);
+    RT_CHECK((ref >> 30) != REF_SPHERE || (ref & 0x3FFFFFFFu) < uint32_t(sc.n_spheres), CHK_BREF);
     if ((ref >> 30) == REF_SPHERE) {
       const uint32_t idx = ref & 0x3FFFFFFFu;
       float r0, r1;
@@ -468,6 +503,7 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
 __device__ __forceinline__ void trav_push(TravState& ts, TravStack& st, int node, float t) {
   // no overflow guard: rt_upload_scene rejects a BVH deeper than kStackDepth, and the stack never holds more
   // entries than the tree has levels
+  RT_CHECK(ts.sp >= 0 && ts.sp < kStackDepth, CHK_STACK_LOCAL);
   st.node[ts.sp] = node;
   st.t[ts.sp] = t;
   ts.sp++;
@@ -484,6 +520,9 @@ __device__ __forceinline__ void trav_push(TravState& ts, TravStack& st, int node
 struct TravStackS {
   uint32_t base;    // address of this thread's level-0 entry
   uint32_t stride;  // bytes between levels = 4 x threads per CTA
+#if RT_CHECKS
+  uint32_t levels;
+#endif
 };
 constexpr int kSmemStackMaxCode = 32767;
 __device__ __forceinline__ int trav_pop(TravState& ts, const TravStackS& st) {
@@ -501,6 +540,10 @@ __device__ __forceinline__ int trav_pop(TravState& ts, const TravStackS& st) {
 }
 __device__ __forceinline__ void trav_push(TravState& ts, TravStackS& st, int node, float t) {
   // entry distances are >= tmin > 0: truncating the mantissa rounds down
+#if RT_CHECKS
+  RT_CHECK(uint32_t(ts.sp) >= st.base && uint32_t(ts.sp) < st.base + st.levels * st.stride, CHK_STACK_SMEM);
+  RT_CHECK(node >= -kSmemStackMaxCode - 1 && node <= kSmemStackMaxCode, CHK_STACK_SMEM);
+#endif
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(uint32_t(ts.sp)), "r"((__float_as_uint(t) & 0xFFFF0000u) | (uint32_t(node) & 0xFFFFu)) : "memory");
   ts.sp += int(st.stride);
 }
@@ -672,9 +715,16 @@ __device__ __forceinline__ void leaf_body(TravState& ts, int leaf, const DeviceS
   const int first = code >> 3, count = (code & 7) + 1;
   const float3 o = ts.o, d = ts.d;
   for (int k = 0; k < count; k++) {
+    RT_CHECK(first + k >= 0 && first + k < sc.n_leaf_refs, CHK_LEAF_REF);
     uint32_t ref = STAGED ? lds_u32(ls.refs + 4u * uint32_t(first + k)) : __ldg(sc.leaf_refs + first + k);
     uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
     float t = -1.0f;
+    if (ref != REF_NONE) {
+      RT_CHECK(type != REF_SPHERE || idx < uint32_t(sc.n_spheres), CHK_SPHERE);
+      RT_CHECK(type != REF_QUAD || idx < uint32_t(sc.n_quads), CHK_QUAD);
+      RT_CHECK(type != REF_BOX || (idx >> 3) < uint32_t(sc.n_boxes), CHK_BOX);
+      RT_CHECK(type != REF_MEDIUM || idx < uint32_t(sc.n_media), CHK_MEDIUM);
+    }
     if (type == REF_SPHERE) {
       const float4 g0 = STAGED ? lds_f4(ls.spheres + 32u * idx) : __ldg(sc.spheres + 2 * idx);
       const float4 g1 = STAGED ? lds_f4(ls.spheres + 32u * idx + 16u) : __ldg(sc.spheres + 2 * idx + 1);
@@ -918,6 +968,7 @@ template <bool COUNT>
 __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p, unsigned int* cn) {
 #pragma unroll 1
   for (int guard = 0; guard < 16; guard++) {
+    RT_CHECK(tex >= 0 && tex < sc.n_textures, CHK_TEXTURE);
     float4 t0 = __ldg(sc.textures + 2 * tex), t1 = __ldg(sc.textures + 2 * tex + 1);
     int kind = __float_as_int(t1.x), a = __float_as_int(t1.y), b = __float_as_int(t1.z);
     if (kind == TEX_SOLID) return xyz(t0);
@@ -935,6 +986,7 @@ __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, 
       v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
       int i = min(int(u * im.y), im.y - 1);
       int j = min(int(v * im.z), im.z - 1);
+      RT_CHECK(i >= 0 && j >= 0 && i < im.y && j < im.z, CHK_TEXEL);
       uchar4 px = __ldg(sc.texels + im.x + j * im.y + i);
       const float s = 1.0f / 255.0f;
       return f3(s * px.x, s * px.y, s * px.z);
@@ -962,6 +1014,10 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
   uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
   s.p = fma3(h.t, d, o);
   s.u = s.v = 0.0f;
+  RT_CHECK(type != REF_SPHERE || idx < uint32_t(sc.n_spheres), CHK_SPHERE);
+  RT_CHECK(type != REF_QUAD || idx < uint32_t(sc.n_quads), CHK_QUAD);
+  RT_CHECK(type != REF_BOX || (idx >> 3) < uint32_t(sc.n_boxes), CHK_BOX);
+  RT_CHECK(type != REF_MEDIUM || idx < uint32_t(sc.n_media), CHK_MEDIUM);
   if (type == REF_SPHERE) {
     float4 g0 = __ldg(sc.spheres + 2 * idx), g1 = __ldg(sc.spheres + 2 * idx + 1);
     int2 meta = __ldg(sc.sph_meta + idx);
@@ -1022,6 +1078,7 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
 template <bool COUNT>
 __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out,
                                             unsigned int* cn) {
+  RT_CHECK(s.material >= 0 && s.material < sc.n_materials, CHK_MATERIAL);
   float4 m0 = __ldg(sc.materials + 2 * s.material), m1 = __ldg(sc.materials + 2 * s.material + 1);
   const int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
   emit = f3(0.0f, 0.0f, 0.0f);

@@ -77,6 +77,7 @@ __device__ __noinline__ int shade_slot(const RenderParams* __restrict__ Pp, floa
   // radiance of a path = beta * (emission | background) at its LAST vertex: no material here both emits and
   // scatters (diffuse_light::scatter is false, material.hpp:36), so no running sum is kept in the pool
   auto deposit = [&](float3 L) {  // the finished sample, quantised to 2^-32, straight into the int64 accumulator
+    RT_CHECK(pixel >= 0 && (unsigned long long)pixel * 3ull + 2ull < P.n_values, CHK_PIXEL);
     unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
     const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
     if (fr) atomicAdd(dst + 0, (unsigned long long)fr);

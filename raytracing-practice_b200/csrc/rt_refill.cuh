@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kRefillThreads, 1) refill_kernel(const __grid_
     ls.refs = opaque_u32(uint32_t(__cvta_generic_to_shared(s_ref)));
   }
   __syncthreads();
-  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes);
+  const NodeSource ns = node_source(s_nodes, P.sc.nodes, P.smem_nodes, P.sc.n_nodes);
   const DeviceScene& sc = P.sc;
   const float INF = __int_as_float(0x7f800000);
   const unsigned FULL = 0xFFFFFFFFu;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kRefillThreads, 1) refill_kernel(const __grid_
           }
         }
         if (!alive) {
+          RT_CHECK(pixel >= 0 && (unsigned long long)pixel * 3ull + 2ull < P.n_values, CHK_PIXEL);
           unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
           const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
           if (fr) atomicAdd(dst + 0, (unsigned long long)fr);

@@ -292,6 +292,7 @@ __device__ __noinline__ int stream_shade_slot(const RenderParams* __restrict__ P
       }
     }
     if (!alive) {
+      RT_CHECK(pixel >= 0 && (unsigned long long)pixel * 3ull + 2ull < P.n_values, CHK_PIXEL);
       unsigned long long* dst = P.accum + 3ull * (unsigned long long)pixel;
       const long long fr = to_fixed(L.x), fg = to_fixed(L.y), fb = to_fixed(L.z);
       if (fr) atomicAdd(dst + 0, (unsigned long long)fr);

@@ -51,6 +51,16 @@ def reduce_accum_to_rank0(accum_tensor):
     return accum_tensor
 
 
+def clear_accum(ctx, cam):
+    """An all-zero accumulator of `cam`'s size — what a rank with an EMPTY sample shard contributes.  (rt_render cannot do
+    it: a sample_count of 0 means "all remaining samples" in the C-ABI.)"""
+    import numpy as np
+
+    from . import image_height
+
+    ctx.upload_accum(cam, np.zeros((image_height(cam), cam.image_width, 3), np.int64))
+
+
 def render_sharded(ctx, cam, seed=0):
     """rt_render of this rank's sample shard, then the reduce.  Rank 0's accumulator holds the image."""
     import torch
@@ -59,6 +69,8 @@ def render_sharded(ctx, cam, seed=0):
     begin, count = shard_samples(cam.samples_per_pixel, rank, world)
     if count > 0:
         ctx.render(cam, seed=seed, sample_begin=begin, sample_count=count, clear=True)
+    else:
+        clear_accum(ctx, cam)  # spp < world: this rank has no samples, but the reduce still needs its (zero) accumulator
     ctx.synchronize()
     if world > 1:
         reduce_accum_to_rank0(ctx.accum_tensor())
@@ -89,18 +101,22 @@ class PeerReduce:
             if self.rank != 0:
                 self.ptr = ctx.peer_open(bytes(t.cpu().tolist()))
 
-    def render(self, seed=0):
-        """One frame: zero the buffer (rank 0), barrier, every rank renders its shard and pushes it, barrier, rank 0 adopts."""
+    def render(self, seed=0, cam=None):
+        """One frame: zero the buffer (rank 0), barrier, every rank renders its shard and pushes it, barrier, rank 0 adopts.
+        `cam`: another camera of the SAME image size (e.g. another sample count); a rank whose shard is empty pushes nothing."""
         import torch
         import torch.distributed as dist
 
-        begin, count = shard_samples(self.cam.samples_per_pixel, self.rank, self.world)
+        cam = self.cam if cam is None else cam
+        begin, count = shard_samples(cam.samples_per_pixel, self.rank, self.world)
         if self.rank == 0:
-            self.ctx.reduce_buffer(self.cam)  # re-zero, same pointer
+            self.ctx.reduce_buffer(cam)  # re-zero, same pointer
         if self.multi:
             dist.barrier()
         if count > 0:
-            self.ctx.render(self.cam, seed=seed, sample_begin=begin, sample_count=count, clear=True, push_accum=self.ptr)
+            self.ctx.render(cam, seed=seed, sample_begin=begin, sample_count=count, clear=True, push_accum=self.ptr)
+        elif self.rank == 0:
+            clear_accum(self.ctx, cam)  # rank 0 adopts below: its own accumulator must exist
         self.ctx.synchronize()
         if self.multi:
             dist.barrier()

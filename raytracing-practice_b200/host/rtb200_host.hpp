@@ -17,12 +17,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <limits>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -994,6 +996,77 @@ inline void checkpoint_save(const char* path, checkpoint_header h, int spp_done,
 }
 }  // namespace rtb200
 
+namespace rtb200 {
+// RT_B200_TIMING=1: camera::render prints where its wall time went (one JSON line on stderr)
+struct phase_timer {
+  std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  std::vector<std::pair<const char*, double>> parts;
+  void mark(const char* name) {
+    const auto now = std::chrono::steady_clock::now();
+    parts.emplace_back(name, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+  void report(int w, int h, int spp, int devices) const {
+    const char* e = std::getenv("RT_B200_TIMING");
+    if (!e || !*e || *e == '0') return;
+    double total = 0;
+    for (const auto& p : parts) total += p.second;
+    std::fprintf(stderr, "RTB200_TIMING {\"width\": %d, \"height\": %d, \"spp\": %d, \"devices\": %d, \"total_ms\": %.3f", w, h, spp, devices, total);
+    for (const auto& p : parts) std::fprintf(stderr, ", \"%s_ms\": %.3f", p.first, p.second);
+    std::fprintf(stderr, "}\n");
+  }
+};
+
+// The process-level context cache of camera::render: slot r of RT_B200_DEVICES keeps its rt_ctx (and, through it, its
+// arena, accumulator, reduce buffer and peer mappings) until the process exits.
+class context_cache {
+ public:
+  static context_cache& get() {
+    static context_cache c;
+    return c;
+  }
+  rt_ctx* acquire(int slot, int device) {
+    if (size_t(slot) >= slots_.size()) slots_.resize(size_t(slot) + 1);
+    entry& e = slots_[size_t(slot)];
+    if (e.ctx && e.device != device) {  // the slot moved to another device: start over for it
+      rt_shutdown(e.ctx);
+      e = entry();
+      for (auto it = peers_.begin(); it != peers_.end();) it = (it->first == slot || it->second == slot) ? peers_.erase(it) : std::next(it);
+    }
+    if (!e.ctx) {
+      int rc = rt_init(device, &e.ctx);
+      if (rc != RT_OK) die(nullptr, "rt_init", rc);
+      e.device = device;
+      // released at exit — registered AFTER the first rt_init, i.e. after the CUDA runtime registered its own exit handler,
+      // so that (handlers run in reverse order) the contexts are shut down while the runtime is still up
+      if (!registered_) registered_ = true, std::atexit(&context_cache::shutdown_all);
+    }
+    return e.ctx;
+  }
+  static void shutdown_all() {
+    context_cache& c = get();
+    for (entry& e : c.slots_)
+      if (e.ctx) rt_shutdown(e.ctx), e.ctx = nullptr;
+    c.peers_.clear();
+  }
+  bool peer_enable(int slot, int with) {
+    if (peers_.count({slot, with})) return true;
+    if (rt_peer_enable(slots_[size_t(slot)].ctx, slots_[size_t(with)].ctx) != RT_OK) return false;
+    peers_.insert({slot, with});
+    return true;
+  }
+
+ private:
+  bool registered_ = false;
+  struct entry {
+    rt_ctx* ctx = nullptr;
+    int device = -1;
+  };
+  std::vector<entry> slots_;
+  std::set<std::pair<int, int>> peers_;
+};
+}  // namespace rtb200
+
 // Environment (the reference's camera has no such fields, and the drop-in keeps its class as it is):
 //   RT_B200_DEVICES         comma-separated CUDA ordinals (default "0"); samples are sharded over them
 //   RT_B200_P6              path of a binary P6 copy of the image
@@ -1023,18 +1096,26 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   if (int(devices.size()) > samples_per_pixel) devices.resize(size_t(std::max(1, samples_per_pixel)));
 
   const int R = int(devices.size());
+  rtb200::phase_timer timing;
+  timing.mark("flatten");
+  // Contexts (CUDA context, stream, scene arena, accumulator, reduce buffer, peer mappings) come from a process-level
+  // cache and are released at exit: a program that renders several scenes or frames — main.cpp's switch run in a loop —
+  // pays rt_init once per device, not once per camera::render (0.2-0.3 s each, more than most of the shipped scenes take
+  // to render).
   std::vector<rt_ctx*> ctx(size_t(R), nullptr);
+  for (int r = 0; r < R; r++) ctx[size_t(r)] = rtb200::context_cache::get().acquire(r, devices[size_t(r)]);
+  timing.mark("init");
   for (int r = 0; r < R; r++) {
-    int rc = rt_init(devices[size_t(r)], &ctx[size_t(r)]);
-    if (rc != RT_OK) rtb200::die(nullptr, "rt_init", rc);
-    rc = rt_upload_scene(ctx[size_t(r)], &sd);
+    int rc = rt_upload_scene(ctx[size_t(r)], &sd);
     if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rc);
   }
+  timing.mark("upload");
   // Several devices: the exchange step (the per-pixel sum of camera.hpp:61) is done on the devices — every context
   // adds its accumulator into the first one's reduce buffer over peer memory (rt_render_opts.push_accum), no host sum.
   // Devices without peer access to the first one fall back to the exact integer sum on the host.
   bool on_device = R > 1;
-  for (int r = 1; r < R && on_device; r++) on_device = rt_peer_enable(ctx[size_t(r)], ctx[0]) == RT_OK;
+  for (int r = 1; r < R && on_device; r++) on_device = rtb200::context_cache::get().peer_enable(r, 0);
+  timing.mark("peer");
 
   const size_t npix = size_t(frame.image_width) * frame.image_height;
   std::vector<int64_t> host_sum;  // the pass's sums when the devices cannot reduce among themselves
@@ -1112,7 +1193,6 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
       std::printf("\rSamples remaining: %d ", samples_per_pixel - done);
       std::fflush(stdout);
       if (stop_after > 0 && done >= stop_after && done < samples_per_pixel) {
-        for (int r = 0; r < R; r++) rt_shutdown(ctx[size_t(r)]);
         std::printf("\rStopped after %d of %d samples per pixel; checkpoint in %s\n", done, samples_per_pixel, ckpt);
         std::exit(3);
       }
@@ -1124,6 +1204,10 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   }
 
   std::vector<uint8_t> rgb(npix * 3);
+  if (!ckpt && (R == 1 || on_device)) {  // (the device passes above are asynchronous when nothing had to wait for them)
+    for (int r = 0; r < R; r++) rt_synchronize(ctx[size_t(r)]);
+  }
+  timing.mark("render");
   if (!sums_on_host) {
     int rc = rt_download(ctx[0], RT_BUF_RGB8, samples_per_pixel, rgb.data(), rgb.size());
     if (rc != RT_OK) rtb200::die(ctx[0], "rt_download", rc);
@@ -1138,13 +1222,16 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
       rgb[i] = uint8_t(int(256 * g));
     }
   }
-  for (int r = 0; r < R; r++) rt_shutdown(ctx[size_t(r)]);
+  timing.mark("download");
 
   rtb200::write_ppm_p3(output_stream, frame.image_width, frame.image_height, rgb.data());
+  output_stream.flush();
   if (const char* p6 = std::getenv("RT_B200_P6")) {
     if (*p6 && !rtb200::write_ppm_p6(p6, frame.image_width, frame.image_height, rgb.data()))
       std::fprintf(stderr, "rtb200: could not write %s\n", p6);
   }
+  timing.mark("ppm");
+  timing.report(frame.image_width, frame.image_height, samples_per_pixel, R);
   std::printf("\rDone.                       \n");
   std::fflush(stdout);
 }

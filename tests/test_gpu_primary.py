@@ -32,23 +32,52 @@ def test_exact_primary_ids_match_reference(rtb, orc, pins, gpu_ctx, name):
     assert np.all(np.isinf(t[~hit]))
 
 
+# Measured on a B200 at every scene's full size (tools/primary_parity.py -> profiles/r2_primary_parity.md): the fp32
+# production traversal picks the reference's primitive on every pixel except exact edge ties of the Cornell walls
+# (64-70 of 360,000 pixels: two quads meet at the pixel centre and fp32 breaks the tie the other way) and 3 grazing pixels
+# of book1_final; quads / boxes hold t to 3e-7, spheres to p99.9 = 5e-5 with a grazing-angle tail up to 1.5e-3 — fp32
+# cannot resolve a radius-1000 sphere's root better (6e-5 absolute on a coordinate of 1000); north_star's 1e-5 is met by
+# the fp64 exact pass above, not by fp32.  The bounds below are those measurements + ~25 % margin.
+ID_MISMATCH_MAX = {"cornell_box": 90, "cornell_rotated": 90, "cornell_smoke": 90, "book1_final": 6}
+T_REL_P999_MAX, T_REL_MAX, N_ABS_P999_MAX = 6.5e-5, 2e-3, 3e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "render"])
 @pytest.mark.parametrize("name", ALL_SCENES)
-def test_fp32_production_traversal_agrees(rtb, orc, gpu_ctx, name):
-    """The fp32 traversal used by rt_render (no fp64 refinement): ids may flip only on a
-    handful of silhouette/edge pixels, t stays close."""
+def test_fp32_production_traversal_agrees(rtb, orc, gpu_ctx, name, mode):
+    """The fp32 traversal rt_render uses (no fp64 refinement), as trace_kernel runs it (`fp32`) and as the RENDER KERNEL
+    ITSELF runs it (`render`: render_kernel's AOV instantiation — its staging, node form, leaf steps, stack and camera-ray
+    arithmetic, rt_b200.h RT_TRACE_RENDER_KERNEL) — camera.hpp:192, hittable_list.hpp:40-64."""
     sc = rtb.Scene(name, rand_seed=1)
     gpu_ctx.upload_scene(sc.desc)
     cam = sc.camera_copy()
-    ids, t, nrm = gpu_ctx.primary_visibility(cam, rtb.RT_TRACE_FP32 | rtb.RT_TRACE_SKIP_MEDIA)
+    flags = (rtb.RT_TRACE_RENDER_KERNEL if mode == "render" else rtb.RT_TRACE_FP32) | rtb.RT_TRACE_SKIP_MEDIA
+    ids, t, nrm = gpu_ctx.primary_visibility(cam, flags)
     oids, ot, onrm = orc.primary(sc.desc, cam, skip_media=True)
     mism = ids != oids
-    assert mism.mean() <= 1e-3, f"{mism.sum()} of {ids.size} pixels differ"
+    assert int(mism.sum()) <= ID_MISMATCH_MAX.get(name, 0), f"{mism.sum()} of {ids.size} pixels differ"
     ok = (~mism) & (oids >= 0)
     rel = np.abs(t[ok] - ot[ok]) / np.abs(ot[ok])
-    assert np.quantile(rel, 0.999) <= 2e-4 and rel.max() <= 1e-2
-    # normals: ignore the few grazing hits on the radius-1000 spheres where fp32 p drifts
+    assert np.quantile(rel, 0.999) <= T_REL_P999_MAX and rel.max() <= T_REL_MAX, (np.quantile(rel, 0.999), rel.max())
     dn = np.abs(nrm[ok] - onrm[ok]).max(axis=1)
-    assert np.quantile(dn, 0.999) <= 2e-3
+    assert np.quantile(dn, 0.999) <= N_ABS_P999_MAX, np.quantile(dn, 0.999)
+    assert np.all(np.isinf(t[(oids < 0) & ~mism]))
+
+
+def test_render_kernel_primary_small_and_ragged(rtb, orc, gpu_ctx):
+    """The AOV instantiation on ragged image sizes (partial 8x4 tiles, width 1) and on a scene whose BVH is NOT fully
+    staged-with-stack (the shared-memory stack variant is chosen per scene): every pixel is written exactly once."""
+    for name in ("quads", "bouncing_spheres"):
+        sc = rtb.Scene(name, rand_seed=1)
+        gpu_ctx.upload_scene(sc.desc)
+        for width, aspect in [(1, 1.0), (7, 16.0 / 9.0), (33, 0.5), (130, 1.7)]:
+            cam = sc.camera_copy(image_width=width, aspect_ratio=aspect)
+            ids, t, nrm = gpu_ctx.primary_visibility(cam, rtb.RT_TRACE_RENDER_KERNEL | rtb.RT_TRACE_SKIP_MEDIA)
+            oids, ot, _ = orc.primary(sc.desc, cam, skip_media=True)
+            assert ids.shape == oids.shape
+            assert (ids != oids).sum() <= 1
+    with pytest.raises(rtb.RtError):
+        gpu_ctx.primary_visibility(cam, rtb.RT_TRACE_RENDER_KERNEL | rtb.RT_TRACE_EXACT)
 
 
 def test_primary_pass_small_widths_and_aspect(rtb, orc, gpu_ctx):

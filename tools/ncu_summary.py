@@ -41,6 +41,36 @@ keys = [
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall: not selected"),
 ]
+# the figures bench.py quotes, tied to the source they were measured on (bench.py omits them when csrc/ has changed)
+try:
+    import glob, hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hh = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(root, "raytracing-practice_b200", "csrc", "*"))):
+        if f.endswith((".cu", ".cuh", ".h", ".hpp")):
+            hh.update(os.path.basename(f).encode())
+            hh.update(open(f, "rb").read())
+    def num(k):
+        return float(m[k][0].replace(",", "")) if k in m and m[k][0] != "" else None
+    def scaled(k):  # ncu prints byte counts with a unit
+        v = num(k)
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(m[k][1], 1) if k in m else 1
+        return None if v is None else v * mult
+    samples = float(os.environ.get("NCU_SAMPLES", "0"))
+    if samples > 0 and os.environ.get("NCU_LATEST", "") == "1":
+        json.dump({"csrc_sha": hh.hexdigest()[:16], "source": os.environ.get("NCU_SOURCE", rep), "kernel": kern, "samples_in_capture": samples,
+                   "dram_bytes_per_sample": (scaled("dram__bytes_read.sum") + scaled("dram__bytes_write.sum")) / samples,
+                   "issue_slot_utilisation": num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                   "active_lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                   "alu_pipe_utilisation": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active") / 100.0,
+                   "fma_pipe_utilisation": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active") / 100.0,
+                   "kernel_ms": scaled("gpu__time_duration.sum") if m.get("gpu__time_duration.sum", ("", ""))[1] == "ms" else num("gpu__time_duration.sum"),
+                   "warp_instructions": num("smsp__inst_executed.sum"),
+                   "l1_hit_rate": num("l1tex__t_sector_hit_rate.pct"), "local_ld_sectors": num("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
+                   "local_st_sectors": num("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum")},
+                  open(os.path.join(root, "profiles", "latest_ncu.json"), "w"), indent=1)
+except Exception as e:  # noqa: BLE001
+    sys.stderr.write(f"latest_ncu.json not written: {e}\n")
 print(f"# {title}\n")
 print(f"Source: `{rep}` (`ncu --set full --clock-control none --import-source on`), kernel `{kern}`.\n")
 print("| metric | value |\n|---|---|")
