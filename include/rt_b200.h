@@ -200,9 +200,13 @@ typedef struct rt_render_opts {
   int32_t sample_count; /*   every pixel; count <= 0 means all of samples_per_pixel    */
   int32_t clear;        /* non-zero: zero the accumulator before rendering             */
   int32_t flags;        /* RT_RENDER_* bits                                            */
-  void* peer_accum;     /* optional: device pointer (own or peer-mapped over NVLink) of
-                           another context's accumulator; when non-NULL the kernel adds
-                           its samples THERE (red.add.u64) instead of locally          */
+  void* peer_accum;     /* optional: the accumulator (rt_accum_device_ptr) of ANOTHER LIVE CONTEXT OF
+                           THIS PROCESS ON THE SAME DEVICE, for a camera of the same image size; when
+                           non-NULL the kernel adds its samples THERE (device-scope red.add.u64)
+                           instead of locally.  Anything else is refused: RT_ERR_INVALID for an
+                           unknown pointer or another image size, RT_ERR_UNSUPPORTED for another
+                           GPU's accumulator (device-scope adds are not atomic across GPUs — use
+                           push_accum there)                                              */
   void* push_accum;     /* optional: a reduce buffer (rt_reduce_buffer of this or another
                            rank, peer-mapped over NVLink): the render accumulates
                            locally and a push kernel, stream-ordered right behind it,

@@ -13,6 +13,7 @@
 // There is no CPU fallback: rt_init fails without a device.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -99,8 +100,11 @@ constexpr int kPoolSmemNodes = RT_POOL_SMEM_NODES;
 constexpr float kFixScale = 4294967296.0f;  // 2^32
 
 __device__ __forceinline__ long long to_fixed(float v) {
-  // NaN -> 0 (a NaN sample would poison the pixel); clamp keeps 2^31 samples from overflowing
-  v = (v == v) ? fminf(fmaxf(v, 0.0f), 1.0e6f) : 0.0f;
+  // NaN -> 0 (a NaN sample would poison the pixel).  The clamp bounds one sample at 2^16 = 65,536 (the brightest
+  // emitter of the shipped scenes is 15; write_color clips the pixel MEAN at 0.999 anyway), so a sample is < 2^48 in
+  // fixed point and the signed 64-bit sum holds 2^15 = 32,768 samples AT the clamp — and 2^31 samples of radiance <= 1
+  // — without wrapping; the headline 10,000 spp fits with every sample at the clamp.
+  v = (v == v) ? fminf(fmaxf(v, 0.0f), 65536.0f) : 0.0f;
   return __float2ll_rn(v * kFixScale);
 }
 
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
           } else {
             pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
           }
-          t = h.t, n = sf.n;
+          t = sf.t, n = sf.n;
         }
         P.aov_id[pixel] = pid, P.aov_t[pixel] = t;
         P.aov_n[3 * pixel] = n.x, P.aov_n[3 * pixel + 1] = n.y, P.aov_n[3 * pixel + 2] = n.z;
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
       } else {
         pid = type == REF_SPHERE ? sc.xspheres[idx].pid : (type == REF_QUAD ? sc.xquads[idx].pid : -2 - int(idx));
       }
-      t = h.t, nx = sf.n.x, ny = sf.n.y, nz = sf.n.z, front = sf.front;
+      t = sf.t, nx = sf.n.x, ny = sf.n.y, nz = sf.n.z, front = sf.front;
     }
   }
   if (P.prim_id) P.prim_id[i] = pid;
@@ -559,6 +563,8 @@ using namespace rtb200;
 namespace {
 std::mutex g_err_mutex;
 std::string g_init_error = "";
+// the live contexts of this process: rt_render_opts.peer_accum must be the accumulator of one of them
+std::vector<struct ::rt_ctx*> g_contexts;
 
 template <typename T>
 struct DevArray {
@@ -802,16 +808,36 @@ int rt_init(int device, rt_ctx** out) {
     delete ctx;
     return RT_ERR_CUDA;
   };
+  const bool timing = std::getenv("RT_B200_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[rt_init] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
+  lap("cudaGetDeviceCount (cuInit)");
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-  cudaDeviceProp prop;
-  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
-  ctx->sm_count = prop.multiProcessorCount;
-  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  lap("cudaSetDevice");
+  // two attributes, not cudaGetDeviceProperties: the full property query costs tens of milliseconds (it reads clocks
+  // and PCI state through the driver) and camera::render pays rt_init once per process
+  int sm_count = 0, smem_optin = 0;
+  if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
+  if ((e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
+  ctx->sm_count = sm_count;
+  ctx->smem_optin = size_t(smem_optin);
+  lap("cudaDeviceGetAttribute x2");
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  lap("cudaStreamCreate (context)");
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->counters, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemset(ctx->counters, 0, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMemset", e);
+  lap("events + counters");
+  {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_contexts.push_back(ctx);
+  }
   *out = ctx;
   return RT_OK;
 }
@@ -819,6 +845,11 @@ int rt_init(int device, rt_ctx** out) {
 void rt_shutdown(rt_ctx* ctx) {
   if (!ctx) return;
   DebugScope dbg("rt_shutdown");
+  {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    for (size_t i = 0; i < g_contexts.size(); i++)
+      if (g_contexts[i] == ctx) g_contexts.erase(g_contexts.begin() + long(i)), i = g_contexts.size();
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_scene(ctx);
@@ -1075,6 +1106,22 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   P.push = static_cast<unsigned long long*>(opts->push_accum);
   P.n_values = (unsigned long long)f.image_width * f.image_height * 3ull;
   if (P.push && opts->peer_accum) return fail(ctx, RT_ERR_INVALID, "peer_accum and push_accum are mutually exclusive");
+  if (opts->peer_accum && opts->peer_accum != ctx->accum) {
+    // The render kernel's per-sample adds are DEVICE-scope atomics (system scope in the hot loop costs every render):
+    // they are only atomic among kernels of one GPU, and nothing in the call says how large the target is.  So the target
+    // must be the accumulator of a live context of this process, on this context's device, of this camera's size;
+    // across GPUs the exchange step is push_accum (system-scope red.add behind the render).
+    const rt_ctx* owner = nullptr;
+    {
+      std::lock_guard<std::mutex> g(g_err_mutex);
+      for (const rt_ctx* c : g_contexts)
+        if (c->accum && c->accum == opts->peer_accum) owner = c;
+    }
+    if (!owner) return fail(ctx, RT_ERR_INVALID, "peer_accum is not the accumulator (rt_accum_device_ptr) of a live context of this process");
+    if (owner->device != ctx->device)
+      return fail(ctx, RT_ERR_UNSUPPORTED, "peer_accum lives on another GPU: the render kernel's adds are device-scope atomics; use push_accum across GPUs");
+    if (owner->accum_values != size_t(P.n_values)) return fail(ctx, RT_ERR_INVALID, "peer_accum belongs to an image of another size");
+  }
 
   P.counters = ctx->counters;
   P.smem_nodes = ctx->smem_nodes;

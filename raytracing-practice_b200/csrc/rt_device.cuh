@@ -1005,14 +1005,56 @@ __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, 
 struct Surface {
   float3 p, n;  // n already flipped against the ray (hit_record::set_face_normal)
   float u, v;
+  float t;      // the hit's ray parameter; with RT_SPHERE_REFINE a sphere root re-solved in fp64
   bool front;
   int material;
 };
+
+#ifndef RT_SPHERE_REFINE
+#define RT_SPHERE_REFINE 2  // 0: fp32 roots as found; 1: fp64 quadratic; 2: one fp64-residual Newton step (default: t within 1e-5 of the
+                            // reference on all but <= 3 pixels per scene instead of on 87-99 % of them, for -1 % on book2_final,
+                            // gpurun_out/ab_refine3.log, profiles/r2_primary_parity.md)
+#endif
+// The root of |o + t d - c|^2 = r^2 nearest to the fp32 root `t32`, solved in fp64 from the same fp32 ray and sphere.
+// fp32 cannot resolve the root on a radius-1000 sphere better than ~5e-5 relative (6e-5 of absolute resolution on a
+// coordinate of 1000, amplified by the cancellation in tca - sqrt(r^2 - l^2)); profiles/r2_primary_parity.md.  Once per
+// SHADED sphere hit (not per candidate): ~45 fp64 instructions.
+// RT_SPHERE_REFINE == 2: one Newton step on f(t) = a t^2 + 2 b t + cc from the fp32 root, with f evaluated in fp64 (the
+// residual is what fp32 cannot see) and the division in fp32 (the correction is ~1e-5 t: seven digits of it are plenty).
+// No fp64 square root or division: ~25 fp64 instructions.  A correction beyond 1e-3 |t| (grazing hit, f' ~ 0) is dropped.
+// Also returns p - c = (o - c) + t d evaluated in fp64: its magnitude is r, not |p|, so the normal (p - c) / r keeps seven
+// digits even for a small sphere far from the origin.
+__device__ __forceinline__ float sphere_root_newton(float3 c32, float r32, float3 o, float3 d, float t32, float3& p_minus_c) {
+  const double ocx = double(o.x) - double(c32.x), ocy = double(o.y) - double(c32.y), ocz = double(o.z) - double(c32.z);
+  const double dx = d.x, dy = d.y, dz = d.z, r = r32, t = t32;
+  const double a = dx * dx + dy * dy + dz * dz, b = ocx * dx + ocy * dy + ocz * dz, cc = ocx * ocx + ocy * ocy + ocz * ocz - r * r;
+  const double at_b = a * t + b;
+  const float f = float((at_b + b) * t + cc), fp = float(2.0 * at_b);
+  const float delta = f * rcp_fast(fp);
+  const float t_new = fabsf(delta) <= 1e-3f * fabsf(t32) ? t32 - delta : t32;
+  const double tn = t_new;
+  p_minus_c = f3(float(ocx + tn * dx), float(ocy + tn * dy), float(ocz + tn * dz));
+  return t_new;
+}
+__device__ __forceinline__ float sphere_root_fp64(float3 c32, float r32, float3 o, float3 d, float t32) {
+  const double cx = c32.x, cy = c32.y, cz = c32.z, r = r32;
+  const double ocx = double(o.x) - cx, ocy = double(o.y) - cy, ocz = double(o.z) - cz;
+  const double dx = d.x, dy = d.y, dz = d.z;
+  const double a = dx * dx + dy * dy + dz * dz, b = ocx * dx + ocy * dy + ocz * dz, cc = ocx * ocx + ocy * ocy + ocz * ocz - r * r;
+  const double disc = b * b - a * cc;
+  if (!(disc >= 0.0)) return t32;  // fp32 saw a grazing hit that fp64 does not: keep it
+  const double sq = sqrt(disc);
+  // both roots without cancellation: q = -(b + sign(b) sqrt(disc)), roots q / a and cc / q
+  const double q = -(b + (b < 0.0 ? -sq : sq));
+  const double r0 = q / a, r1 = q != 0.0 ? cc / q : r0;
+  return float(fabs(r0 - double(t32)) <= fabs(r1 - double(t32)) ? r0 : r1);
+}
 
 __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, float3 o, float3 d, float time) {
   Surface s;
   uint32_t type = h.ref >> 30, idx = h.ref & 0x3FFFFFFFu;
   s.p = fma3(h.t, d, o);
+  s.t = h.t;
   s.u = s.v = 0.0f;
   RT_CHECK(type != REF_SPHERE || idx < uint32_t(sc.n_spheres), CHK_SPHERE);
   RT_CHECK(type != REF_QUAD || idx < uint32_t(sc.n_quads), CHK_QUAD);
@@ -1022,7 +1064,17 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
     float4 g0 = __ldg(sc.spheres + 2 * idx), g1 = __ldg(sc.spheres + 2 * idx + 1);
     int2 meta = __ldg(sc.sph_meta + idx);
     float3 c = fma3(time, xyz(g1), xyz(g0));
+#if RT_SPHERE_REFINE == 2
+    float3 pc;
+    s.t = sphere_root_newton(c, g0.w, o, d, h.t, pc);
+    float3 outward = rcp_fast(g0.w) * pc;
+#elif RT_SPHERE_REFINE
+    s.t = sphere_root_fp64(c, g0.w, o, d, h.t);
+    s.p = fma3(s.t, d, o);
     float3 outward = rcp_fast(g0.w) * (s.p - c);
+#else
+    float3 outward = rcp_fast(g0.w) * (s.p - c);
+#endif
     s.p = fma3(g0.w, outward, c);  // re-project onto the sphere: removes the O(t*eps) drift of o + t d
     s.material = meta.x;
     float4 m1 = __ldg(sc.materials + 2 * meta.x + 1);

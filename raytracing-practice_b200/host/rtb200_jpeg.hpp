@@ -159,6 +159,9 @@ class jpeg_decoder {
       for (int l = 1; l <= 16; l++) {
         h.valptr[l] = k;
         h.mincode[l] = code;
+        // Kraft check: the canonical codes of length l must fit l bits (stb_image rejects such tables too); without it
+        // an over-subscribed table (e.g. bits[1] = 200) walks `first` past the 512-entry lookup table
+        if (code + h.bits[l] > (1 << l)) return fail("bad DHT: over-subscribed code lengths");
         for (int j = 0; j < h.bits[l]; j++, k++, code++) {
           if (l <= 9) {
             int first = code << (9 - l);
@@ -208,8 +211,10 @@ class jpeg_decoder {
     for (int l = 10; l <= 16; l++) {
       int c = code >> (16 - l);
       if (h.maxcode[l] >= 0 && c <= h.maxcode[l] && c >= h.mincode[l]) {
+        const int at = h.valptr[l] + c - h.mincode[l];
+        if (at < 0 || at > 255) break;  // (cannot happen for a table that passed read_dht; kept as a bound on vals[])
         skip(l);
-        return h.vals[h.valptr[l] + c - h.mincode[l]];
+        return h.vals[at];
       }
     }
     bad_code_ = true;

@@ -35,11 +35,14 @@ def test_exact_primary_ids_match_reference(rtb, orc, pins, gpu_ctx, name):
 # Measured on a B200 at every scene's full size (tools/primary_parity.py -> profiles/r2_primary_parity.md): the fp32
 # production traversal picks the reference's primitive on every pixel except exact edge ties of the Cornell walls
 # (64-70 of 360,000 pixels: two quads meet at the pixel centre and fp32 breaks the tie the other way) and 3 grazing pixels
-# of book1_final; quads / boxes hold t to 3e-7, spheres to p99.9 = 5e-5 with a grazing-angle tail up to 1.5e-3 — fp32
-# cannot resolve a radius-1000 sphere's root better (6e-5 absolute on a coordinate of 1000); north_star's 1e-5 is met by
-# the fp64 exact pass above, not by fp32.  The bounds below are those measurements + ~25 % margin.
+# of book1_final.  t: quads / boxes 3e-7; sphere roots get one fp64-residual Newton step when they are shaded
+# (RT_SPHERE_REFINE, rt_device.cuh) and sit at p99.9 <= 2.1e-6 with at most 3 pixels per scene beyond north_star's 1e-5
+# (grazing hits, max 1.5e-3) — without the step fp32 leaves 12-26 % of the sphere pixels beyond 1e-5 (p99.9 = 5e-5).
+# Normals: p99.9 <= 1.7e-5, a few hundred pixels per scene beyond 1e-5 — the fp32 rounding of the ray DIRECTION (6e-8)
+# moves the hit point on a radius-0.2 sphere at distance 10 by that much; only fp64 rays (the exact pass above) remove it.
+# The bounds below are those measurements + ~25 % margin.
 ID_MISMATCH_MAX = {"cornell_box": 90, "cornell_rotated": 90, "cornell_smoke": 90, "book1_final": 6}
-T_REL_P999_MAX, T_REL_MAX, N_ABS_P999_MAX = 6.5e-5, 2e-3, 3e-5
+T_REL_P999_MAX, T_REL_MAX, T_OVER_1E5_MAX, N_ABS_P999_MAX = 3e-6, 4e-3, 6, 2.2e-5
 
 
 @pytest.mark.parametrize("mode", ["fp32", "render"])
@@ -59,6 +62,7 @@ def test_fp32_production_traversal_agrees(rtb, orc, gpu_ctx, name, mode):
     ok = (~mism) & (oids >= 0)
     rel = np.abs(t[ok] - ot[ok]) / np.abs(ot[ok])
     assert np.quantile(rel, 0.999) <= T_REL_P999_MAX and rel.max() <= T_REL_MAX, (np.quantile(rel, 0.999), rel.max())
+    assert int((rel > 1e-5).sum()) <= T_OVER_1E5_MAX, int((rel > 1e-5).sum())
     dn = np.abs(nrm[ok] - onrm[ok]).max(axis=1)
     assert np.quantile(dn, 0.999) <= N_ABS_P999_MAX, np.quantile(dn, 0.999)
     assert np.all(np.isinf(t[(oids < 0) & ~mism]))

@@ -85,6 +85,13 @@ def test_peer_accumulation_two_contexts(rtb, gpu_ctx):
     other.render(cam, seed=8, sample_begin=20, sample_count=28, peer_accum=ptr)
     other.synchronize()
     assert np.array_equal(gpu_ctx.download_accum(), whole)
+    # the target must be a live context's accumulator of this image size (rt_b200.h): anything else is refused, not written to
+    with pytest.raises(rtb.RtError):
+        other.render(cam, seed=8, peer_accum=ptr + 64)
+    small = sc.camera_copy(image_width=48, samples_per_pixel=4)
+    with pytest.raises(rtb.RtError):
+        other.render(small, seed=8, peer_accum=ptr)
+    assert np.array_equal(gpu_ctx.download_accum(), whole)
     other.close()
 
 

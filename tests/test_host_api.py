@@ -85,6 +85,34 @@ def test_jpeg_decoder_subsampled_and_restart_files(rtb, built, tmp_path):
         assert np.array_equal(got, want), tag
 
 
+def test_jpeg_decoder_rejects_malformed_huffman_tables(rtb, built, tmp_path):
+    """A crafted DHT whose code-length counts over-subscribe the code space (bits[1] = 200, stb_image rejects it too) must
+    be refused by read_dht's Kraft check — before the fix the canonical-code loop wrote past the 512-entry lookup table —
+    and truncated / garbage files must fail cleanly: rtw_image then falls back to its cyan texel (rtw_stb_image.hpp)."""
+    Image = pytest.importorskip("PIL.Image")
+    path = str(tmp_path / "ok.jpg")
+    Image.fromarray((np.random.default_rng(1).random((16, 16, 3)) * 255).astype(np.uint8)).save(path, quality=80)
+    data = bytearray(open(path, "rb").read())
+    i = data.find(b"\xff\xc4")  # the first DHT segment: marker, length (2), Tc/Th (1), 16 counts
+    assert i > 0
+    lib = rtb.scenes_lib()
+    p, w, h = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int()
+    for tag, mutate in [("oversubscribed", lambda d: d.__setitem__(i + 5, 200)), ("all_ones", lambda d: d.__setitem__(slice(i + 5, i + 21), bytes([255] * 16))),
+                        ("truncated", lambda d: d.__delitem__(slice(len(d) // 2, len(d)))), ("garbage", lambda d: d.__setitem__(slice(2, 40), bytes(range(38))))]:
+        d = bytearray(data)
+        mutate(d)
+        bad = str(tmp_path / f"{tag}.jpg")
+        open(bad, "wb").write(bytes(d))
+        rc = lib.rth_load_texture(bad.encode(), 0, C.byref(p), C.byref(w), C.byref(h))
+        if tag in ("oversubscribed", "all_ones", "garbage"):
+            assert rc != 0, tag  # refused, no crash
+        elif rc == 0:  # a truncated scan may still decode (missing data reads as zero bits): must not crash, size intact
+            assert (w.value, h.value) == (16, 16)
+            lib.rth_free(p)
+    assert lib.rth_load_texture(path.encode(), 0, C.byref(p), C.byref(w), C.byref(h)) == 0
+    lib.rth_free(p)
+
+
 def test_scene_converter_counts_and_errors(rtb, built):
     lib = C.CDLL(rtb.CUDA_LIB_PATH)
     lib.rt_debug_build_stats.argtypes = [C.POINTER(rtb.rt_scene_desc), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
