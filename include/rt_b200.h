@@ -218,8 +218,9 @@ enum {
   RT_RENDER_DEFAULT = 0,
   RT_RENDER_COUNTERS = 1,  /* instrumented kernel: also fills rt_stats.census (slower; not for timing) */
   RT_RENDER_MEGAKERNEL = 2, /* force the one-path-per-lane megakernel (render_kernel)               */
-  RT_RENDER_POOL = 4,       /* force the per-warp path-pool kernel (pool_kernel); with neither bit the
-                               library picks (env RT_B200_KERNEL=mega|pool|stream|refill overrides the default) */
+  /* 4: was RT_RENDER_POOL, the per-warp path-pool kernel (removed: 0.55-0.65x the megakernel; rt_render answers
+        RT_ERR_UNSUPPORTED to the bit).  With no kernel bit the library's default renders (the megakernel; the
+        process environment RT_B200_KERNEL=mega|stream|refill, read once at rt_init, can move the default) */
   RT_RENDER_STREAM = 8,     /* force the streaming kernel (stream_kernel: CTA-wide ray queues, lanes refilled
                                mid-traversal); RT_ERR_UNSUPPORTED when the scene does not fit its
                                shared-memory plan                                                   */

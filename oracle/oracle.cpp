@@ -257,8 +257,8 @@ bool medium_hit(const Scene& s, const rt_hittable& h, const Ray& r, double tmin,
   rec.n = mk(1, 0, 0);
   rec.front = true;
   rec.mat = h.material;
-  rec.u = rec1.u;  // the book leaves u,v untouched; the record starts as a copy-less local, so
-  rec.v = rec1.v;  // define them as the entry hit's (only an image-textured phase would care)
+  rec.u = 0;  // the book leaves u, v unset (the record is an uninitialised local of ray_color): defined as 0, 0, as in
+  rec.v = 0;  // ref_ext.hpp and in the device's surface_at — only an image-textured phase function can tell
   rec.prim = -1;
   return true;
 }

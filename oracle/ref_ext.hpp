@@ -115,8 +115,9 @@ public:
     rec.normal = vec3(1, 0, 0);
     rec.front_face = true;
     rec.mat = phase_function;
-    rec.u = rec1.u; // harness convention: inherit the entry hit's uv (book leaves them unset)
-    rec.v = rec1.v;
+    rec.u = 0; // the book leaves u, v unset (ray_color's record is an uninitialised local): defined here as 0, 0 — the
+    rec.v = 0; // convention of this repo's device code (surface_at, medium branch) and of oracle.cpp; only a uv-dependent
+               // (image) phase-function texture can tell, and the reference has neither class
     return true;
   }
 

@@ -66,7 +66,6 @@ struct RenderParams {
   int* aov_id;             // render_kernel<.., AOV>: primitive id, t and shading normal of every pixel-centre ray
   float* aov_t;
   float* aov_n;
-  float* pool_cold;  // pool kernel with RT_POOL_COLD_GLOBAL: the shade-only words of every path
   StreamLayout sl;   // streaming kernel only
 };
 
@@ -81,22 +80,16 @@ constexpr int kRenderThreads = RT_THREADS;
 #define RT_SMEM_STACK 1  // traversal stacks in shared memory when the launch has the room (rt_device.cuh, TravStackS)
 #endif
 constexpr size_t kSmemStackBudget = size_t(RT_SMEM_STACK_BUDGET_KB) * 1024;
-#ifndef RT_DEFAULT_POOL
-#define RT_DEFAULT_POOL 0
-#endif
-constexpr bool kDefaultPoolKernel = RT_DEFAULT_POOL != 0;
 #ifndef RT_DEFAULT_STREAM
 #define RT_DEFAULT_STREAM 0
 #endif
 constexpr bool kDefaultStreamKernel = RT_DEFAULT_STREAM != 0;
+enum : int { KERNEL_MEGA = 0, KERNEL_STREAM = 1, KERNEL_REFILL = 2 };
+constexpr int RT_RENDER_POOL_REMOVED = 4;  // rt_b200.h: the bit of the removed path-pool kernel
 #ifndef RT_DEFAULT_REFILL
 #define RT_DEFAULT_REFILL 0
 #endif
 constexpr bool kDefaultRefillKernel = RT_DEFAULT_REFILL != 0;
-#ifndef RT_POOL_SMEM_NODES
-#define RT_POOL_SMEM_NODES 256
-#endif
-constexpr int kPoolSmemNodes = RT_POOL_SMEM_NODES;
 constexpr float kFixScale = 4294967296.0f;  // 2^32
 
 __device__ __forceinline__ long long to_fixed(float v) {
@@ -337,7 +330,6 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
 }
 
 }  // namespace rtb200
-#include "rt_pool.cuh"
 #include "rt_stream.cuh"
 #include "rt_refill.cuh"
 namespace rtb200 {
@@ -577,6 +569,15 @@ struct rt_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  // Process-environment knobs (experiments and test hooks, none needed for normal use), read ONCE when the context is
+  // created: rt_render itself never looks at the environment, its behaviour is a function of its arguments and the context.
+  //   RT_B200_KERNEL=mega|stream|refill  default render kernel        RT_B200_NO_STAGING=1   BVH top levels only in shared memory
+  //   RT_B200_CHUNK_MAX=n                samples per work item <= n   RT_B200_MAX_CHUNKS=n   launches of <= n sample chunks (test hook)
+  struct Knobs {
+    int kernel = 0;
+    int chunk_max = 0, max_chunks = 0;
+    bool no_staging = false;
+  } knobs;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -598,7 +599,6 @@ struct rt_ctx {
   unsigned long long rays_total = 0, samples_total = 0;
   int smem_nodes = 0;
   int launches = 0;
-  void* pool_cold = nullptr;  // pool kernel, RT_POOL_COLD_GLOBAL builds only
   void* scratch = nullptr;  // rt_download's device-side staging buffer
   size_t scratch_bytes = 0;
   unsigned long long* reduce_buf = nullptr;  // fused multi-GPU reduce: peers add their accumulators here
@@ -817,6 +817,14 @@ int rt_init(int device, rt_ctx** out) {
     t_last = now;
   };
   lap("cudaGetDeviceCount (cuInit)");
+  ctx->knobs.kernel = kDefaultStreamKernel ? KERNEL_STREAM : (kDefaultRefillKernel ? KERNEL_REFILL : KERNEL_MEGA);
+  if (const char* k = std::getenv("RT_B200_KERNEL")) {
+    const std::string v = k;
+    ctx->knobs.kernel = v == "stream" ? KERNEL_STREAM : (v == "refill" ? KERNEL_REFILL : (v == "mega" ? KERNEL_MEGA : ctx->knobs.kernel));
+  }
+  if (const char* k = std::getenv("RT_B200_CHUNK_MAX")) ctx->knobs.chunk_max = std::max(1, std::atoi(k));
+  if (const char* k = std::getenv("RT_B200_MAX_CHUNKS")) ctx->knobs.max_chunks = std::max(1, std::atoi(k));
+  ctx->knobs.no_staging = std::getenv("RT_B200_NO_STAGING") != nullptr;
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   lap("cudaSetDevice");
   // two attributes, not cudaGetDeviceProperties: the full property query costs tens of milliseconds (it reads clocks
@@ -856,7 +864,6 @@ void rt_shutdown(rt_ctx* ctx) {
   cudaFree(ctx->arena);
   cudaFreeHost(ctx->staging);
   cudaFree(ctx->accum);
-  cudaFree(ctx->pool_cold);
   cudaFree(ctx->reduce_buf);
   cudaFree(ctx->scratch);
   cudaFree(ctx->counters);
@@ -947,7 +954,7 @@ static MegaPlan plan_megakernel(const rt_ctx* ctx, RenderParams& P) {
   const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
   constexpr size_t kStateBytes = size_t(32) * kRenderThreads;  // per-thread shade state (render_kernel)
   MegaPlan mp;
-  mp.all_smem = staged + kStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+  mp.all_smem = staged + kStateBytes + 4096 <= ctx->smem_optin && !ctx->knobs.no_staging;
   size_t smem;
   if (mp.all_smem) {
     P.smem_nodes = ctx->sc.n_nodes, smem = staged;
@@ -1051,7 +1058,7 @@ int rt_render(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_opts* opts
   const long long count = opts->sample_count > 0 ? opts->sample_count : (long long)cam->samples_per_pixel - opts->sample_begin;
   const unsigned long long per_chunk = (unsigned long long)((f.image_width + 7) / 8) * (unsigned long long)((f.image_height + 3) / 4) * 32ull;
   unsigned long long max_chunks = (0xFFFFFFFFull - (unsigned long long)ctx->sm_count * kRenderThreads - 1ull) / per_chunk;
-  if (const char* e = std::getenv("RT_B200_MAX_CHUNKS")) max_chunks = std::min<unsigned long long>(max_chunks, std::max(1, std::atoi(e)));  // test hook
+  if (ctx->knobs.max_chunks > 0) max_chunks = std::min<unsigned long long>(max_chunks, (unsigned long long)ctx->knobs.max_chunks);  // test hook
   if (max_chunks == 0) return fail(ctx, RT_ERR_INVALID, "image too large (more than 2^32 pixels per launch)");
   const long long cap = (long long)std::min<unsigned long long>(max_chunks * 32ull, 1ull << 30);
   if (count <= cap) return render_range(ctx, cam, opts, true, true);
@@ -1094,7 +1101,7 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   long long total = (long long)f.image_width * f.image_height * P.sample_count;
   long long chunk = total / (threads * 8);
   long long chunk_max = 32;
-  if (const char* e = std::getenv("RT_B200_CHUNK_MAX")) chunk_max = std::max(1, std::atoi(e));  // A/B knob (tools/ab_env.py)
+  if (ctx->knobs.chunk_max > 0) chunk_max = ctx->knobs.chunk_max;  // A/B knob (tools/ab_env.py)
   P.chunk = int(std::max<long long>(1, std::min<long long>({chunk, chunk_max, (long long)P.sample_count})));
   while (P.chunk & (P.chunk - 1)) P.chunk &= P.chunk - 1;  // largest power of two below: the megakernel finds the end of an item with a mask
   P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
@@ -1127,21 +1134,16 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
   P.smem_nodes = ctx->smem_nodes;
   size_t smem = size_t(P.smem_nodes) * 64;
   const bool count = (opts->flags & RT_RENDER_COUNTERS) != 0;
-  // kernel choice: the per-warp path-pool kernel (rt_pool.cuh) unless the megakernel is asked for
-  bool pool = kDefaultPoolKernel;
-  if (const char* e = std::getenv("RT_B200_KERNEL")) pool = std::string(e) == "pool" ? true : (std::string(e) == "mega" ? false : pool);
-  if (opts->flags & RT_RENDER_MEGAKERNEL) pool = false;
-  if (opts->flags & RT_RENDER_POOL) pool = true;
-  // the streaming kernel (rt_stream.cuh) when the scene fits its shared-memory plan
-  bool stream = kDefaultStreamKernel && !pool;
-  if (const char* e = std::getenv("RT_B200_KERNEL")) stream = std::string(e) == "stream" ? true : (std::string(e) == "mega" || std::string(e) == "pool" ? false : stream);
-  if (opts->flags & (RT_RENDER_MEGAKERNEL | RT_RENDER_POOL)) stream = false;
-  if (opts->flags & RT_RENDER_STREAM) stream = true, pool = false;
-  // the in-place-refill kernel (rt_refill.cuh)
-  bool refill = kDefaultRefillKernel && !pool && !stream;
-  if (const char* e = std::getenv("RT_B200_KERNEL")) refill = std::string(e) == "refill" ? true : (std::string(e) == "mega" || std::string(e) == "pool" || std::string(e) == "stream" ? false : refill);
-  if (opts->flags & (RT_RENDER_MEGAKERNEL | RT_RENDER_POOL | RT_RENDER_STREAM)) refill = false;
-  if (opts->flags & RT_RENDER_REFILL) refill = true, pool = stream = false;
+  // kernel choice: the megakernel unless another scheduling variant is asked for (rt_render_opts.flags; the library-wide
+  // default can be moved with RT_B200_KERNEL, read once at rt_init) — all of them produce the same accumulator bits
+  if (opts->flags & RT_RENDER_POOL_REMOVED)
+    return fail(ctx, RT_ERR_UNSUPPORTED, "the per-warp path-pool kernel was removed (0.55-0.65x the megakernel); its queue-fed successor is RT_RENDER_STREAM");
+  int kernel = ctx->knobs.kernel;
+  if (opts->flags & RT_RENDER_MEGAKERNEL) kernel = KERNEL_MEGA;
+  if (opts->flags & RT_RENDER_STREAM) kernel = KERNEL_STREAM;
+  if (opts->flags & RT_RENDER_REFILL) kernel = KERNEL_REFILL;
+  bool stream = kernel == KERNEL_STREAM;
+  const bool refill = kernel == KERNEL_REFILL;
   StreamLayout SL;
   std::memset(&SL, 0, sizeof SL);
   if (stream && !stream_layout(ctx, ctx->host.bvh_depth, SL)) {
@@ -1164,7 +1166,7 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     ctx->launches++;
   } else if (refill) {
     const size_t staged = size_t(ctx->sc.n_nodes) * 64 + size_t(ctx->sc.n_spheres) * 32 + size_t(ctx->sc.n_boxes) * 48 + size_t(ctx->sc.n_leaf_refs) * 4;
-    const bool all_smem = staged + kRefillStateBytes + 4096 <= ctx->smem_optin && !std::getenv("RT_B200_NO_STAGING");
+    const bool all_smem = staged + kRefillStateBytes + 4096 <= ctx->smem_optin && !ctx->knobs.no_staging;
     if (all_smem) {
       P.smem_nodes = ctx->sc.n_nodes, smem = staged;
     } else {
@@ -1180,29 +1182,6 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
     kern<<<grid, kRefillThreads, smem, ctx->stream>>>(P);
     RT_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-  } else if (pool) {
-    // work items of a power-of-two number of samples (the kernel finds the end of an item with a mask)
-    int c2 = 1;
-    while (c2 * 2 <= P.chunk) c2 *= 2;
-    P.chunk = c2;
-    P.n_chunks = (P.sample_count + P.chunk - 1) / P.chunk;
-    const unsigned long long items = (unsigned long long)P.per_chunk * (unsigned long long)P.n_chunks;
-    if (items >= 0xFFFFFFFFull) return fail(ctx, RT_ERR_INVALID, "image x samples too large for one launch: shard the samples");
-    P.n_items = unsigned(items);
-    const size_t pool_bytes = pool_smem_bytes(kRenderThreads);
-    if (ctx->smem_optin < pool_bytes + 4096) return fail(ctx, RT_ERR_UNSUPPORTED, "not enough shared memory for the path pools");
-    // only the very top of the BVH is staged: the pools want the shared memory, and L1 (what is left of the
-    // 256 KB) holds the hot nodes just as well — measured, gpurun_out/ab_smem_nodes.log
-    P.smem_nodes = int(std::min<size_t>({size_t(ctx->sc.n_nodes), size_t(kPoolSmemNodes), (ctx->smem_optin - 2048 - pool_bytes) / 64}));
-    if (const char* e = std::getenv("RT_B200_SMEM_NODES")) P.smem_nodes = std::min(P.smem_nodes, std::max(0, std::atoi(e)));  // experiments: L1 vs shared
-    smem = size_t(P.smem_nodes) * 64 + pool_bytes;
-    if (pool_cold_global_bytes(grid, kRenderThreads) && !ctx->pool_cold) RT_CUDA(ctx, cudaMalloc(&ctx->pool_cold, pool_cold_global_bytes(grid, kRenderThreads)));
-    P.pool_cold = static_cast<float*>(ctx->pool_cold);
-    const unsigned long long zero = 0ull;  // items are handed out from 0
-    RT_CUDA(ctx, cudaMemcpyAsync(ctx->counters, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->stream));
-    RT_CUDA(ctx, cudaFuncSetAttribute(count ? pool_kernel<true> : pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    RT_CUDA(ctx, launch_render(count ? pool_kernel<true> : pool_kernel<false>, grid, smem, ctx->stream, P));
     ctx->launches++;
   } else {
     // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared

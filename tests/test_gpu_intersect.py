@@ -159,5 +159,5 @@ def test_large_scene_bvh_beyond_shared_memory(rtb, orc, gpu_ctx):
     cam = su.camera(width=160, spp=8, depth=6, lookfrom=(0, 0, 70), vfov=60.0)
     gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_MEGAKERNEL)
     a, r = gpu_ctx.download_accum(), gpu_ctx.stats().rays
-    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_POOL)
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_REFILL)
     assert np.array_equal(a, gpu_ctx.download_accum()) and r == gpu_ctx.stats().rays and a.any()

@@ -207,26 +207,6 @@ def test_cpp_drop_in_camera_render(rtb, gpu_ctx, tmp_path):
         assert np.array_equal(img, gpu_ctx.download_rgb8(40).astype(np.int64))
 
 
-@pytest.mark.parametrize("name,width,spp", [("book2_final", 160, 48), ("cornell_smoke", 96, 40), ("bouncing_spheres", 200, 24), ("earth", 120, 16)])
-def test_pool_kernel_is_bit_identical_to_the_megakernel(rtb, gpu_ctx, name, width, spp):
-    """Both render kernels (one path per lane / per-warp path pool, csrc/rt_pool.cuh) use the same Philox
-    keys and the same fixed-point sums: same accumulator bits, same ray count, also on a sample shard."""
-    sc = rtb.Scene(name, rand_seed=1)
-    cam = sc.camera_copy(image_width=width, samples_per_pixel=spp)
-    gpu_ctx.upload_scene(sc.desc)
-    out = {}
-    for tag, flags in (("mega", rtb.RT_RENDER_MEGAKERNEL), ("pool", rtb.RT_RENDER_POOL)):
-        gpu_ctx.render(cam, seed=11, flags=flags)
-        out[tag] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
-        gpu_ctx.render(cam, seed=11, flags=flags, sample_begin=5, sample_count=7)
-        out[tag + "_shard"] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
-    assert out["mega"][1] == out["pool"][1] and np.array_equal(out["mega"][0], out["pool"][0])
-    assert out["mega_shard"][1] == out["pool_shard"][1] and np.array_equal(out["mega_shard"][0], out["pool_shard"][0])
-    cam.max_depth = 0
-    gpu_ctx.render(cam, seed=11, flags=rtb.RT_RENDER_POOL)
-    assert not gpu_ctx.download_accum().any() and gpu_ctx.stats().rays == 0
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("kernel", ["stream", "refill"])
 @pytest.mark.parametrize("name,width,spp", [("book2_final", 160, 48), ("cornell_smoke", 96, 40), ("book1_final", 200, 24), ("perlin_sphere", 120, 16)])
@@ -246,6 +226,11 @@ def test_scheduling_variants_are_bit_identical_to_the_megakernel(rtb, gpu_ctx, k
         out[tag + "_shard"] = (gpu_ctx.download_accum(), gpu_ctx.stats().rays)
     assert out["mega"][1] == out["alt"][1] and np.array_equal(out["mega"][0], out["alt"][0])
     assert out["mega_shard"][1] == out["alt_shard"][1] and np.array_equal(out["mega_shard"][0], out["alt_shard"][0])
+    cam.max_depth = 0  # ray_color returns black at once (camera.hpp:183-186): nothing is launched
+    gpu_ctx.render(cam, seed=13, flags=flag)
+    assert not gpu_ctx.download_accum().any() and gpu_ctx.stats().rays == 0
+    with pytest.raises(rtb.RtError):  # the bit of the removed path-pool kernel
+        gpu_ctx.render(cam, seed=13, flags=4)
 
 
 def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
@@ -283,7 +268,7 @@ def test_box_primitive_equals_its_six_quads(rtb, gpu_ctx, monkeypatch):
 def test_peer_reduce_push_accum(rtb, gpu_ctx):
     """The multi-GPU exchange step without a collective (rt_render_opts.push_accum): three 'ranks' (contexts) render
     disjoint sample shards, behind each render a push kernel adds the rank's accumulator into rank 0's reduce buffer;
-    the adopted image has the bits of a single render.  Both render kernels; the buffer is reusable."""
+    the adopted image has the bits of a single render.  Two of the render kernels; the buffer is reusable."""
     sc = rtb.Scene("cornell_smoke", rand_seed=1)
     cam = sc.camera_copy(image_width=120, samples_per_pixel=36, max_depth=10)
     gpu_ctx.upload_scene(sc.desc)
@@ -292,7 +277,7 @@ def test_peer_reduce_push_accum(rtb, gpu_ctx):
     others = [rtb.Context(0), rtb.Context(0)]
     for o in others:
         o.upload_scene(sc.desc)
-    for flags in (rtb.RT_RENDER_MEGAKERNEL, rtb.RT_RENDER_POOL):
+    for flags in (rtb.RT_RENDER_MEGAKERNEL, rtb.RT_RENDER_REFILL):
         ptr, handle = gpu_ctx.reduce_buffer(cam)
         assert len(handle) == 64 and any(handle)
         for ctx, (b, n) in zip([gpu_ctx] + others, [(0, 10), (10, 7), (17, 19)]):
@@ -316,16 +301,22 @@ def test_oversized_render_is_split_into_launches(rtb, gpu_ctx, monkeypatch):
     gpu_ctx.upload_scene(sc.desc)
     gpu_ctx.render(cam, seed=6)
     whole, st = gpu_ctx.download_accum(), gpu_ctx.stats()
-    launches0 = st.kernel_launches
-    monkeypatch.setenv("RT_B200_MAX_CHUNKS", "2")  # 64 samples per launch -> 3 launches
-    gpu_ctx.render(cam, seed=6)
-    st2 = gpu_ctx.stats()
-    assert np.array_equal(gpu_ctx.download_accum(), whole) and st2.rays == st.rays and st2.samples == st.samples
+    monkeypatch.setenv("RT_B200_MAX_CHUNKS", "2")  # 64 samples per launch -> 3 launches; knobs are read when a context is created
+    small = rtb.Context(0)
+    small.upload_scene(sc.desc)
+    launches0 = small.stats().kernel_launches
+    small.render(cam, seed=6)
+    st2 = small.stats()
+    assert np.array_equal(small.download_accum(), whole) and st2.rays == st.rays and st2.samples == st.samples
     assert st2.kernel_launches - launches0 == 3
-    ptr, _ = gpu_ctx.reduce_buffer(cam)
-    gpu_ctx.render(cam, seed=6, push_accum=ptr, flags=rtb.RT_RENDER_POOL)
-    gpu_ctx.adopt_reduce_buffer()
-    assert np.array_equal(gpu_ctx.download_accum(), whole)
+    ptr, _ = small.reduce_buffer(cam)
+    small.render(cam, seed=6, push_accum=ptr, flags=rtb.RT_RENDER_REFILL)
+    small.adopt_reduce_buffer()
+    assert np.array_equal(small.download_accum(), whole)
+    small.close()
+    launches1 = gpu_ctx.stats().kernel_launches  # the session's context was created without the knob: one launch
+    gpu_ctx.render(cam, seed=6)
+    assert gpu_ctx.stats().kernel_launches - launches1 == 1
 
 
 @pytest.mark.parametrize("width,aspect,spp", [(1, 1.0, 1), (7, 7 / 5, 3), (33, 16 / 9, 1), (257, 4.0, 2)])
@@ -341,7 +332,7 @@ def test_ragged_image_sizes_and_tiny_jobs(rtb, gpu_ctx, width, aspect, spp):
     gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_MEGAKERNEL)
     a, st = gpu_ctx.download_accum(), gpu_ctx.stats()
     assert a.shape == (h, width, 3) and st.samples == width * h * spp and st.rays >= st.samples
-    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_POOL)
+    gpu_ctx.render(cam, seed=2, flags=rtb.RT_RENDER_REFILL)
     assert np.array_equal(gpu_ctx.download_accum(), a) and gpu_ctx.stats().rays == st.rays
     # one sample at a time, accumulated: same bits
     for s in range(spp):

@@ -91,3 +91,32 @@ def test_earth_texture_through_named_scene(rtb, orc, gpu_ctx, pins):
     got = gpu_ctx.eval_texture(tex, uvp)
     want = orc.texture_value(sc.desc, tex, uvp)
     assert np.all(np.abs(got - want) < 1e-6, axis=1).mean() >= 0.999
+
+
+def test_textured_phase_function_of_a_medium(rtb, orc, gpu_ctx):
+    """constant_medium with a TEXTURED isotropic phase function (the book only ever uses a solid colour, and its medium
+    hit leaves rec.u / rec.v unset): this repo defines u = v = 0 for a medium hit — device surface_at, oracle.cpp and
+    oracle/ref_ext.hpp alike — so an image texture reads its (u, v) = (0, 0) texel and a checker follows the scatter
+    point.  The converged GPU image must match the oracle's for both."""
+    rng = np.random.default_rng(5)
+    img = np.zeros((4, 4, 3), np.uint8)
+    img[:] = (40, 200, 90)
+    img[3, 0] = (250, 60, 20)  # the texel at (u, v) = (0, 0): v is flipped (texture.hpp:109), row 3
+    for kind in ("image", "checker"):
+        s = su.SceneDesc()
+        tex = s.image(img) if kind == "image" else s.checker(1.3, s.solid(0.9, 0.2, 0.1), s.solid(0.1, 0.3, 0.9))
+        fog = s.medium(s.sphere((0, 0, 0), 2.0, s.dielectric(1.5)), 1.5, s.isotropic(tex))
+        floor = s.quad((-6, -2.2, -6), (12, 0, 0), (0, 0, 12), s.lambertian(s.solid(0.5, 0.5, 0.5)))
+        desc = s.finish(s.list([fog, floor]))
+        cam = su.camera(width=64, spp=2048, depth=12, lookfrom=(0, 1, 9), vfov=35.0)
+        gpu_ctx.upload_scene(desc)
+        gpu_ctx.render(cam, seed=3)
+        got = gpu_ctx.download_radiance(cam.samples_per_pixel).astype(np.float64)
+        mean, var, _ = orc.render_linear(desc, cam, spp=256, seed=9)
+        var_tot = var * (1.0 + 256 / 2048)
+        for c in range(3):
+            z = (got[..., c].sum() - mean[..., c].sum()) / np.sqrt(var_tot[..., c].sum() + 1e-30)
+            assert abs(z) < 5.0, (kind, c, z)
+        centre = got[24:40, 24:40].mean(axis=(0, 1))  # the fog ball: its colour is the texture's
+        if kind == "image":
+            assert centre[0] > 1.5 * centre[1], centre  # the reddish (0, 0) texel, not the green rest of the image

@@ -1,6 +1,6 @@
 """Another render kernel vs the megakernel on the GPU: bit-exact accumulator check + timing, for the in-tree library and every
 variant build (build/variants/*.so from tools/ab_variants.py).
-  python tools/ab_kern.py refill|stream|pool scene1,scene2 spp [width]        (under gpurun)"""
+  python tools/ab_kern.py refill|stream scene1,scene2 spp [width]        (under gpurun)"""
 import glob, importlib, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,7 +27,7 @@ if sys.argv[-1] == "child":  # one library
             return ctx.download_accum(), st.rays, round(st.samples / best / 1e3, 1)
         a0, r0, v0 = run(rtb.RT_RENDER_MEGAKERNEL)
         try:
-            a1, r1, v1 = run({"stream": rtb.RT_RENDER_STREAM, "pool": rtb.RT_RENDER_POOL, "refill": rtb.RT_RENDER_REFILL}[KERN])
+            a1, r1, v1 = run({"stream": rtb.RT_RENDER_STREAM, "refill": rtb.RT_RENDER_REFILL}[KERN])
             same = bool(np.array_equal(a0, a1)) and r0 == r1
             out[name] = [v0, v1, "same" if same else f"DIFF px={int((a0 != a1).any(axis=2).sum())} rays {r0} vs {r1} sum {int(a0.sum())} vs {int(a1.sum())}"]
         except rtb.RtError as e:

@@ -12,7 +12,7 @@ if len(sys.argv) > 4:
 cam = sc.camera_copy(**over)
 ctx = rtb.Context(0)
 ctx.upload_scene(sc.desc)
-flags = {"mega": rtb.RT_RENDER_MEGAKERNEL, "pool": rtb.RT_RENDER_POOL, "count": rtb.RT_RENDER_COUNTERS, "stream": rtb.RT_RENDER_STREAM, "refill": rtb.RT_RENDER_REFILL}.get(kern, 0)
+flags = {"mega": rtb.RT_RENDER_MEGAKERNEL, "count": rtb.RT_RENDER_COUNTERS, "stream": rtb.RT_RENDER_STREAM, "refill": rtb.RT_RENDER_REFILL}.get(kern, 0)
 ctx.render(cam, seed=5, flags=flags)
 st = ctx.stats()
 print(f"{name} {kern}: {st.samples / st.last_render_ms / 1e3:.1f} Msamples/s, {st.rays / st.last_render_ms / 1e3:.1f} Mrays/s, {st.last_render_ms:.2f} ms")

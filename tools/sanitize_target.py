@@ -30,7 +30,7 @@ for name, depth in (("book2_final", 40), ("cornell_smoke", 50), ("bouncing_spher
     ctx.trace_rays(o, d, None, 0.001, np.inf, rtb.RT_TRACE_EXACT)
     # every render kernel, same bits
     acc = {}
-    for tag, flags in (("mega", rtb.RT_RENDER_MEGAKERNEL), ("pool", rtb.RT_RENDER_POOL), ("stream", rtb.RT_RENDER_STREAM), ("refill", rtb.RT_RENDER_REFILL),
+    for tag, flags in (("mega", rtb.RT_RENDER_MEGAKERNEL), ("stream", rtb.RT_RENDER_STREAM), ("refill", rtb.RT_RENDER_REFILL),
                        ("mega+count", rtb.RT_RENDER_MEGAKERNEL | rtb.RT_RENDER_COUNTERS), ("refill+count", rtb.RT_RENDER_REFILL | rtb.RT_RENDER_COUNTERS)):
         try:
             ctx.render(cam, seed=9, flags=flags)
