@@ -261,11 +261,19 @@ __device__ __forceinline__ bool box_roots(float4 b0, float4 b1, float4 b2, float
 // ---------------------------------------------------------------------------------------
 // BVH node access: the first `smem_nodes` nodes (breadth-first = top levels) live in shared
 // memory, the rest is read through the read-only path (L1/L2 resident: the arrays are tiny).
+#ifndef RT_NODE_CH
+#define RT_NODE_CH 2  // staged BVH nodes as (centre, half extent), node_step without per-axis min / max: +4..5.5 % on the BVH-heavy scenes, same accumulators (gpurun_out/ab_ch1.log, ab_ss1.log); 0 = the (lo, hi) form
+#endif
+#ifndef RT_NODE_PLANAR
+#define RT_NODE_PLANAR 0  // 1: fully staged BVHs keep the four quarters of the node records in four planes (bank spreading)
+#endif
+static_assert(!RT_NODE_PLANAR || RT_NODE_CH, "planar staging is implemented on the (centre, half extent) staging path");
 struct NodeSource {
   const float4* smem;
   const float4* gmem;
   int smem_nodes;
   uint32_t smem_addr;  // 32-bit shared-window address of `smem`, see node_source()
+  uint32_t plane;      // RT_NODE_PLANAR: bytes per plane = 16 x staged nodes
 #if RT_CHECKS
   int n_nodes;
 #endif
@@ -276,9 +284,9 @@ __device__ __forceinline__ NodeSource node_source(const float4* smem, const floa
   uint32_t a = uint32_t(__cvta_generic_to_shared(smem));
   asm volatile("mov.u32 %0, %0;" : "+r"(a));
 #if RT_CHECKS
-  return NodeSource{smem, gmem, smem_nodes, a, n_nodes};
+  return NodeSource{smem, gmem, smem_nodes, a, 16u * uint32_t(smem_nodes), n_nodes};
 #else
-  return NodeSource{smem, gmem, smem_nodes, a};
+  return NodeSource{smem, gmem, smem_nodes, a, 16u * uint32_t(smem_nodes)};
 #endif
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -306,7 +314,13 @@ template <bool ALL_SMEM = false>
 __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4& a, float4& b, float4& c, int& c0, int& c1) {
   float4 dd;
   RT_CHECK(idx >= 0 && idx < ns.n_nodes, CHK_NODE);
-  if (ALL_SMEM || idx < ns.smem_nodes) {
+  if (RT_NODE_PLANAR && ALL_SMEM) {
+    // planar staging (stage_nodes): quarter q of every record in its own plane, so the 16-byte reads a warp makes of 32
+    // random nodes spread over all eight 16-byte bank groups (idx & 7) instead of the two a 64-byte record allows
+    const uint32_t p = ns.smem_addr + 16u * uint32_t(idx);
+    a = lds_f4(p), b = lds_f4(p + ns.plane), c = lds_f4(p + 2u * ns.plane);
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dd.x), "=f"(dd.y) : "r"(ns.smem_addr + 3u * ns.plane + 8u * uint32_t(idx)));
+  } else if (ALL_SMEM || idx < ns.smem_nodes) {
     // 32-bit shared-window address: through the generic pointer the compiler rebuilt the window base
     // (S2R CgaCtaId, MOV, LEA, LEA) at every node step
     const uint32_t p = ns.smem_addr + 64u * uint32_t(idx);
@@ -320,9 +334,6 @@ __device__ __forceinline__ void load_node(const NodeSource& ns, int idx, float4&
   c1 = __float_as_int(dd.y);
 }
 
-#ifndef RT_NODE_CH
-#define RT_NODE_CH 2  // staged BVH nodes as (centre, half extent), node_step without per-axis min / max: +4..5.5 % on the BVH-heavy scenes, same accumulators (gpurun_out/ab_ch1.log, ab_ss1.log); 0 = the (lo, hi) form
-#endif
 // Copies the first `n` BVH node records into shared memory.  With RT_NODE_CH and a fully staged BVH every (lo, hi) pair
 // becomes (centre, half extent) on the way, rounded so that [c - h, c + h] contains [lo, hi]: the box the traversal sees
 // never shrinks.
@@ -338,7 +349,13 @@ __device__ __forceinline__ void stage_nodes(float4* s_nodes, const float4* __res
       float4 a = g_nodes[4 * i], b = g_nodes[4 * i + 1], c = g_nodes[4 * i + 2];
       ch(a.x, a.w), ch(a.y, b.x), ch(a.z, b.y);  // child 0: x, y, z
       ch(b.z, c.y), ch(b.w, c.z), ch(c.x, c.w);  // child 1
-      s_nodes[4 * i] = a, s_nodes[4 * i + 1] = b, s_nodes[4 * i + 2] = c, s_nodes[4 * i + 3] = g_nodes[4 * i + 3];
+      if (RT_NODE_PLANAR) {
+        const float4 dd = g_nodes[4 * i + 3];
+        s_nodes[i] = a, s_nodes[n + i] = b, s_nodes[2 * n + i] = c;
+        reinterpret_cast<float2*>(s_nodes + 3 * n)[i] = make_float2(dd.x, dd.y);
+      } else {
+        s_nodes[4 * i] = a, s_nodes[4 * i + 1] = b, s_nodes[4 * i + 2] = c, s_nodes[4 * i + 3] = g_nodes[4 * i + 3];
+      }
     }
   } else {
     for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) s_nodes[i] = g_nodes[i];
@@ -452,6 +469,9 @@ constexpr int kTravDone = int(0x80000000u);
 #endif
 #ifndef RT_NODE_THR
 #define RT_NODE_THR 1
+#endif
+#ifndef RT_KEYFN_NODE_THR
+#define RT_KEYFN_NODE_THR 1  // > 1: the render kernel's traversal prefers leaf steps while fewer lanes than this want a node step
 #endif
 #ifndef RT_SPECULATIVE
 #define RT_SPECULATIVE 0  // 1: speculative while-while (node_step_spec); measured 0.88x on book2_final, 0.96-1.00x elsewhere (gpurun_out/ab_spec.log)
@@ -906,6 +926,29 @@ __device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const No
     trav_reset(ts, st);
     ts.cur = 0;
   }
+#if RT_KEYFN_NODE_THR > 1
+  // node steps while at least RT_KEYFN_NODE_THR lanes want one; below that the lanes waiting on a leaf go first (they
+  // come back with fresh node work), and only when no lane sits on a leaf do the stragglers step alone
+  for (;;) {
+    const unsigned bn = __ballot_sync(FULL, ts.cur >= 0);
+    if (__popc(bn) >= RT_KEYFN_NODE_THR) {
+#pragma unroll
+      for (int u = 0; u < RT_NODE_UNROLL; u++)
+        if (ts.cur >= 0) node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
+      continue;
+    }
+    const unsigned busy = __ballot_sync(FULL, ts.cur != kTravDone);
+    if (busy == 0u) break;
+    if (busy & ~bn) {
+      if (ts.cur < 0 && ts.cur != kTravDone) {
+        aux_of(ts.time, ts.skip);
+        leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, key_of, cn, ls);
+      }
+    } else {
+      if (ts.cur >= 0) node_step<COUNT, ALL_SMEM>(ts, st, ns, cn);
+    }
+  }
+#else
   for (;;) {
     while (__any_sync(FULL, ts.cur >= 0)) {
 #pragma unroll
@@ -918,6 +961,7 @@ __device__ __forceinline__ Hit closest_hit_keyfn(const DeviceScene& sc, const No
       leaf_step<COUNT, false, ALL_SMEM>(ts, st, sc, media, key_of, cn, ls);
     }
   }
+#endif
   return ts.best;
 }
 

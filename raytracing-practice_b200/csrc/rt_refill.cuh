@@ -28,7 +28,7 @@ namespace rtb200 {
 #define RT_REFILL_SHADE_THR 20  // leave the traversal once this many lanes wait for a shade
 #endif
 #ifndef RT_REFILL_NODE_THR
-#define RT_REFILL_NODE_THR 8  // node step while at least this many lanes want one, else the lanes on a leaf go first
+#define RT_REFILL_NODE_THR 1  // node step while at least this many lanes want one, else the lanes on a leaf go first (8 measured slower than 1: leaf steps are the expensive ones, gpurun_out/refill_ab1.log, ab_thr.log)
 #endif
 #ifndef RT_REFILL_THREADS
 #define RT_REFILL_THREADS RT_THREADS
