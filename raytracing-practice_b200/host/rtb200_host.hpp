@@ -26,6 +26,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_b200.h"
@@ -1043,6 +1044,32 @@ class context_cache {
     }
     return e.ctx;
   }
+  // all slots of one camera::render at once: the contexts that do not exist yet are created CONCURRENTLY, one thread per
+  // device — creating a CUDA context takes 0.4-1.7 s and eight of them in a row would outlast the headline render eight times
+  std::vector<rt_ctx*> acquire_all(const std::vector<int>& devices) {
+    const size_t R = devices.size();
+    if (slots_.size() < R) slots_.resize(R);
+    std::vector<size_t> missing;
+    for (size_t r = 0; r < R; r++) {
+      entry& e = slots_[r];
+      if (e.ctx && e.device != devices[r]) acquire(int(r), devices[r]);  // the slot moved: the serial path replaces it
+      if (!slots_[r].ctx) missing.push_back(r);
+    }
+    if (missing.size() > 1) {
+      std::vector<int> rc(R, RT_OK);
+      std::vector<std::thread> workers;
+      for (size_t r : missing) workers.emplace_back([this, r, &devices, &rc] { rc[r] = rt_init(devices[r], &slots_[r].ctx); });
+      for (std::thread& w : workers) w.join();
+      for (size_t r : missing) {
+        if (rc[r] != RT_OK) die(nullptr, "rt_init", rc[r]);
+        slots_[r].device = devices[r];
+      }
+      if (!registered_) registered_ = true, std::atexit(&context_cache::shutdown_all);
+    }
+    std::vector<rt_ctx*> out(R, nullptr);
+    for (size_t r = 0; r < R; r++) out[r] = acquire(int(r), devices[r]);
+    return out;
+  }
   static void shutdown_all() {
     context_cache& c = get();
     for (entry& e : c.slots_)
@@ -1102,12 +1129,18 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   // cache and are released at exit: a program that renders several scenes or frames — main.cpp's switch run in a loop —
   // pays rt_init once per device, not once per camera::render (0.2-0.3 s each, more than most of the shipped scenes take
   // to render).
-  std::vector<rt_ctx*> ctx(size_t(R), nullptr);
-  for (int r = 0; r < R; r++) ctx[size_t(r)] = rtb200::context_cache::get().acquire(r, devices[size_t(r)]);
+  std::vector<rt_ctx*> ctx = rtb200::context_cache::get().acquire_all(devices);
   timing.mark("init");
-  for (int r = 0; r < R; r++) {
-    int rc = rt_upload_scene(ctx[size_t(r)], &sd);
-    if (rc != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rc);
+  if (R == 1) {
+    int rc = rt_upload_scene(ctx[0], &sd);
+    if (rc != RT_OK) rtb200::die(ctx[0], "rt_upload_scene", rc);
+  } else {  // the BVH build + upload of every device's copy, concurrently (rt_upload_scene is synchronous)
+    std::vector<int> rcs(size_t(R), RT_OK);
+    std::vector<std::thread> workers;
+    for (int r = 0; r < R; r++) workers.emplace_back([&, r] { rcs[size_t(r)] = rt_upload_scene(ctx[size_t(r)], &sd); });
+    for (std::thread& w : workers) w.join();
+    for (int r = 0; r < R; r++)
+      if (rcs[size_t(r)] != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rcs[size_t(r)]);
   }
   timing.mark("upload");
   // Several devices: the exchange step (the per-pixel sum of camera.hpp:61) is done on the devices — every context
