@@ -470,6 +470,9 @@ constexpr int kTravDone = int(0x80000000u);
 #ifndef RT_NODE_THR
 #define RT_NODE_THR 1
 #endif
+#ifndef RT_POP_BOTH
+#define RT_POP_BOTH 0
+#endif
 #ifndef RT_KEYFN_NODE_THR
 #define RT_KEYFN_NODE_THR 1  // > 1: the render kernel's traversal prefers leaf steps while fewer lanes than this want a node step
 #endif
@@ -512,10 +515,21 @@ struct TravStack {
 __device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
   while (ts.sp > 0) {
     ts.sp--;
+#if RT_POP_BOTH
+    // both words of the entry are requested together (the volatile read cannot be sunk below the test): one local-memory
+    // latency per pop instead of two in a row — the pop loop runs at ~5 lanes and is latency, not issue (12 % of the PC
+    // samples for 7 % of the instructions, profiles/r22_render_final.md)
+    const int node = *reinterpret_cast<const volatile int*>(&st.node[ts.sp]);
+    if (st.t[ts.sp] <= ts.best.t) {
+      ts.cur = node;
+      return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
+    }
+#else
     if (st.t[ts.sp] <= ts.best.t) {
       ts.cur = st.node[ts.sp];
       return ts.cur >= 0 ? MODE_NODE : MODE_LEAF;
     }
+#endif
   }
   ts.cur = kTravDone;
   return MODE_SHADE;  // traversal finished: ts.best is the answer
