@@ -471,8 +471,10 @@ constexpr int kTravDone = int(0x80000000u);
 #define RT_NODE_THR 1
 #endif
 #ifndef RT_POP_BOTH
-#define RT_POP_BOTH 0
+#define RT_POP_BOTH 1  // the pop requests both words of a stack entry together: +2.4..3 % on book2_final, others unchanged (gpurun_out/ab_pop.log)
 #endif
+// (Tried on top of it: the newest entry cached in two registers until the next push — most pops then touch no memory — is
+//  bit-identical and -7 % on book2_final: the two registers cost more than the latency, gpurun_out/ab_tc.log.)
 #ifndef RT_KEYFN_NODE_THR
 #define RT_KEYFN_NODE_THR 1  // > 1: the render kernel's traversal prefers leaf steps while fewer lanes than this want a node step
 #endif
@@ -512,7 +514,7 @@ struct TravStack {
 };
 
 // pop, skipping subtrees that start beyond the current closest hit
-__device__ __forceinline__ int trav_pop(TravState& ts, const TravStack& st) {
+__device__ __forceinline__ int trav_pop(TravState& ts, TravStack& st) {
   while (ts.sp > 0) {
     ts.sp--;
 #if RT_POP_BOTH
@@ -559,7 +561,7 @@ struct TravStackS {
 #endif
 };
 constexpr int kSmemStackMaxCode = 32767;
-__device__ __forceinline__ int trav_pop(TravState& ts, const TravStackS& st) {
+__device__ __forceinline__ int trav_pop(TravState& ts, TravStackS& st) {
   while (uint32_t(ts.sp) != st.base) {
     ts.sp -= int(st.stride);
     uint32_t e;
@@ -581,8 +583,8 @@ __device__ __forceinline__ void trav_push(TravState& ts, TravStackS& st, int nod
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(uint32_t(ts.sp)), "r"((__float_as_uint(t) & 0xFFFF0000u) | (uint32_t(node) & 0xFFFFu)) : "memory");
   ts.sp += int(st.stride);
 }
-__device__ __forceinline__ void trav_reset(TravState& ts, const TravStack&) { ts.sp = 0; }
-__device__ __forceinline__ void trav_reset(TravState& ts, const TravStackS& st) { ts.sp = int(st.base); }
+__device__ __forceinline__ void trav_reset(TravState& ts, TravStack&) { ts.sp = 0; }
+__device__ __forceinline__ void trav_reset(TravState& ts, TravStackS& st) { ts.sp = int(st.base); }
 
 // 1/d with +-huge instead of +-inf so that 0 * inf never produces NaN in the slab test
 __device__ __forceinline__ void trav_set_ray(TravState& ts, float3 o, float3 d, float time, float tmin, uint32_t skip) {
@@ -798,7 +800,7 @@ __device__ __forceinline__ void leaf_body(TravState& ts, int leaf, const DeviceS
   }
 }
 template <bool COUNT, bool CALLFREE = false, bool STAGED = false, typename KeyFn, typename Stack = TravStack>
-__device__ __forceinline__ int leaf_step(TravState& ts, const Stack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
+__device__ __forceinline__ int leaf_step(TravState& ts, Stack& st, const DeviceScene& sc, bool media, KeyFn key_of, unsigned int* cn,
                                          const LeafSource& ls = LeafSource{0u, 0u, 0u}) {
   leaf_body<COUNT, CALLFREE, STAGED>(ts, ts.cur, sc, media, key_of, cn, ls);
   return trav_pop(ts, st);
@@ -816,7 +818,8 @@ __device__ __forceinline__ Hit closest_hit_prepared(const DeviceScene& sc, const
   const unsigned FULL = 0xFFFFFFFFu;
   TravStack st;
   int mode = MODE_DONE;
-  if (active) ts.sp = 0, ts.cur = 0, mode = MODE_NODE;
+  trav_reset(ts, st);
+  if (active) ts.cur = 0, mode = MODE_NODE;
 #if RT_NODE_THR == 1
   for (;;) {  // while-while: node steps while ANY lane wants one (one vote per step), then one leaf step for the rest
     while (__any_sync(FULL, mode == MODE_NODE))
@@ -866,6 +869,7 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene& sc, const NodeSour
   ts.best = Hit{tmax, REF_NONE};
   ts.cur = kTravDone;
   if (active) trav_begin<COUNT>(ts, sc, o, d, time, tmin, tmax, skip_ref, media, key, bounce, cn);
+  trav_reset(ts, st);
 #if RT_SPECULATIVE
   int pend = kTravDone;  // the parked leaf, kTravDone = none
   for (;;) {

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kRefillThreads, 1) refill_kernel(const __grid_
   // what a lane carries in registers across BOTH phases: the traversal's position and two flags
   TravState ts;
   TravStack st;
-  ts.cur = kTravDone, ts.sp = 0;
+  ts.cur = kTravDone;
+  trav_reset(ts, st);
   bool alive = false;  // the lane's path has a ray (being traced, or traced and waiting for its shade)
   bool done = false;   // the image has no samples left for this lane
 
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(kRefillThreads, 1) refill_kernel(const __grid_
         }
         sts_f4(st_a + kStC, make_float4(o.x, o.y, o.z, best.t));
         sts_f4(st_a + kStD, make_float4(d.x, d.y, d.z, __uint_as_float(best.ref)));
-        ts.cur = 0, ts.sp = 0;
+        ts.cur = 0;
+        trav_reset(ts, st);
       }
     }
     const unsigned out_of_work = __ballot_sync(FULL, done);
