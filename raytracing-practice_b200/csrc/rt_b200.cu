@@ -934,6 +934,20 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.n_global_media = int(h.global_media.size());
   for (int i = 0; i < 4; i++) s.global_media[i] = i < s.n_global_media ? h.global_media[size_t(i)] : -1;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#if RT_CHECKS
+  // Self-test of the checks build (tools/sanitize.sh): RT_B200_CHECK_SELFTEST=1 plants ONE out-of-range reference — the first
+  // sphere reference of the leaf list is pointed one past the end of the sphere array — which the device-side checks must
+  // report (site CHK_SPHERE) at the next rt_synchronize.  The read it causes lands in the array staged next to the spheres:
+  // garbage in the image, no fault.
+  if (std::getenv("RT_B200_CHECK_SELFTEST") && s.n_spheres > 0) {
+    for (size_t i = 0; i < h.leaf_refs.size(); i++)
+      if (h.leaf_refs[i] != REF_NONE && (h.leaf_refs[i] >> 30) == REF_SPHERE) {
+        const uint32_t bad = make_ref(REF_SPHERE, uint32_t(s.n_spheres));
+        RT_CUDA(ctx, cudaMemcpy(const_cast<uint32_t*>(s.leaf_refs) + i, &bad, sizeof bad, cudaMemcpyHostToDevice));
+        break;
+      }
+  }
+#endif
   // top of the BVH in shared memory: as many breadth-first nodes as fit beside the static needs
   size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 0;
   ctx->smem_nodes = int(std::min<size_t>(size_t(s.n_nodes), budget / 64));

@@ -22,8 +22,9 @@ namespace rtb200 {
 // compute-sanitizer is closed on this GPU pool, so the library carries its own bounds checks: in a checks build every
 // dynamically indexed access of the kernels (BVH nodes, leaf references, primitive / material / texture / texel arrays,
 // both traversal stacks, the accumulator) is tested against its array's size; a failure records its site code in
-// g_rt_check_fail (largest code wins) and the access is clamped, and the next rt_synchronize / rt_get_stats returns
-// RT_ERR_CUDA naming the site.  Product builds compile none of it.
+// g_rt_check_fail (largest code wins) and the next rt_synchronize returns RT_ERR_CUDA naming the site (the access itself
+// still happens: the check reports, it does not repair).  RT_B200_CHECK_SELFTEST=1 plants one bad reference at upload so
+// that the mechanism itself can be seen to fire.  Product builds compile none of it.
 #ifndef RT_CHECKS
 #define RT_CHECKS 0
 #endif

@@ -17,6 +17,9 @@ compute-sanitizer --tool memcheck python -c "print(1)" > $OUT/compute_sanitizer_
 rc=0
 RT_B200_LIB=build/variants/checks.so RT_B200_DEBUG=1 python tools/sanitize_target.py > $OUT/checks_build.log 2>&1 || rc=1
 echo "checks build: rc=$rc, $(grep -c 'device-side checks evaluated' $OUT/checks_build.log) synchronisations reported, failures: $(grep -c 'worst failing site [1-9]' $OUT/checks_build.log)"
+# the checks themselves must fire: one planted out-of-range sphere reference -> rt_synchronize reports site 5 (CHK_SPHERE)
+RT_B200_LIB=build/variants/checks.so RT_B200_CHECK_SELFTEST=1 SAN_SELFTEST=1 python tools/sanitize_target.py > $OUT/checks_selftest.log 2>&1
+if grep -q "device-side bounds check failed at site 5" $OUT/checks_selftest.log; then echo "checks self-test: the planted bad reference was reported (site 5 = CHK_SPHERE)"; else echo "checks self-test: NOT reported"; rc=1; fi
 for i in 1 2 3; do
   SAN_HASH=1 python tools/sanitize_target.py > $OUT/product_run$i.log 2>&1 || rc=1
 done

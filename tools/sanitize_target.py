@@ -13,6 +13,16 @@ WIDTH = int(os.environ.get("SAN_WIDTH", "64"))
 SPP = int(os.environ.get("SAN_SPP", "4"))
 ctx = rtb.Context(0)
 rng = np.random.default_rng(3)
+if os.environ.get("SAN_SELFTEST"):  # a checks build with RT_B200_CHECK_SELFTEST=1: the planted bad reference must be reported
+    sc = rtb.Scene("bouncing_spheres", rand_seed=1)
+    ctx.upload_scene(sc.desc)
+    ctx.render(sc.camera_copy(image_width=64, samples_per_pixel=2, max_depth=8), seed=1)
+    try:
+        ctx.synchronize()
+        print("SELFTEST: nothing reported")
+    except rtb.RtError as e:
+        print("SELFTEST:", e)
+    sys.exit(0)
 for name, depth in (("book2_final", 40), ("cornell_smoke", 50), ("bouncing_spheres", 20), ("perlin_sphere", 10), ("earth", 10), ("quads", 10)):
     sc = rtb.Scene(name, rand_seed=1)
     cam = sc.camera_copy(image_width=WIDTH, samples_per_pixel=SPP, max_depth=depth)
