@@ -50,15 +50,8 @@ HASH_SPP = 32  # the GPU-count-invariance job: sample indices 0..31 of every pix
 
 
 def csrc_sha():
-    import glob
-    import hashlib
-
-    h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "raytracing-practice_b200", "csrc", "*"))):
-        if f.endswith((".cu", ".cuh", ".h", ".hpp")):
-            h.update(os.path.basename(f).encode())
-            h.update(open(f, "rb").read())
-    return h.hexdigest()[:16]
+    """sha256 of the CODE of csrc/ (comments / whitespace removed) — raytracing-practice_b200/csrc_sha.py."""
+    return importlib.import_module("raytracing-practice_b200.csrc_sha").csrc_sha(ROOT)
 
 
 def latest_ncu():

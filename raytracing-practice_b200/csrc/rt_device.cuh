@@ -472,10 +472,11 @@ constexpr int kTravDone = int(0x80000000u);
 #define RT_NODE_THR 1
 #endif
 #ifndef RT_POP_BOTH
-#define RT_POP_BOTH 1  // the pop requests both words of a stack entry together: +2.4..3 % on book2_final, others unchanged (gpurun_out/ab_pop.log)
+#define RT_POP_BOTH 1  // +1.3..3 % on book2_final over five A/B runs, other scenes unchanged (gpurun_out/ab_pop.log, ab_pair.log, ab_pair2.log) — see trav_pop
 #endif
-// (Tried on top of it: the newest entry cached in two registers until the next push — most pops then touch no memory — is
-//  bit-identical and -7 % on book2_final: the two registers cost more than the latency, gpurun_out/ab_tc.log.)
+// (Also measured on the stack: 64-bit {node, distance} entries, one LDL.64 per pop: +-0 %; the newest entry cached in two
+//  registers until the next push — most pops then touch no memory —: -7 % on book2_final, the two registers cost more than
+//  the latency, gpurun_out/ab_tc.log.  All bit-identical.)
 #ifndef RT_KEYFN_NODE_THR
 #define RT_KEYFN_NODE_THR 1  // > 1: the render kernel's traversal prefers leaf steps while fewer lanes than this want a node step
 #endif
@@ -519,9 +520,11 @@ __device__ __forceinline__ int trav_pop(TravState& ts, TravStack& st) {
   while (ts.sp > 0) {
     ts.sp--;
 #if RT_POP_BOTH
-    // both words of the entry are requested together (the volatile read cannot be sunk below the test): one local-memory
-    // latency per pop instead of two in a row — the pop loop runs at ~5 lanes and is latency, not issue (12 % of the PC
-    // samples for 7 % of the instructions, profiles/r22_render_final.md)
+    // Written to request both words of the entry together (the pop loop is 12 % of the PC samples for 7 % of the
+    // instructions, profiles/r22_render_final.md).  It does not: NVVM still sinks this load below the distance test — the
+    // pop loop's SASS is unchanged — and a real pairing (LDL.64 entries) measures +-0.  What the edit does change is the
+    // register allocation of the surrounding loop, and THAT build is reproducibly 1.3-3 % faster on book2_final: kept as a
+    // measured code-generation effect, not as a mechanism.
     const int node = *reinterpret_cast<const volatile int*>(&st.node[ts.sp]);
     if (st.t[ts.sp] <= ts.best.t) {
       ts.cur = node;

@@ -45,11 +45,9 @@ keys = [
 try:
     import glob, hashlib, json, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    hh = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(root, "raytracing-practice_b200", "csrc", "*"))):
-        if f.endswith((".cu", ".cuh", ".h", ".hpp")):
-            hh.update(os.path.basename(f).encode())
-            hh.update(open(f, "rb").read())
+    sys.path.insert(0, root)
+    import importlib
+    code_sha = importlib.import_module("raytracing-practice_b200.csrc_sha").csrc_sha(root)
     def num(k):
         return float(m[k][0].replace(",", "")) if k in m and m[k][0] != "" else None
     def scaled(k):  # ncu prints byte counts with a unit
@@ -58,7 +56,7 @@ try:
         return None if v is None else v * mult
     samples = float(os.environ.get("NCU_SAMPLES", "0"))
     if samples > 0 and os.environ.get("NCU_LATEST", "") == "1":
-        json.dump({"csrc_sha": hh.hexdigest()[:16], "source": os.environ.get("NCU_SOURCE", rep), "kernel": kern, "samples_in_capture": samples,
+        json.dump({"csrc_sha": code_sha, "source": os.environ.get("NCU_SOURCE", rep), "kernel": kern, "samples_in_capture": samples,
                    "dram_bytes_per_sample": (scaled("dram__bytes_read.sum") + scaled("dram__bytes_write.sum")) / samples,
                    "issue_slot_utilisation": num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
                    "active_lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
