@@ -426,3 +426,23 @@ def test_cpp_checkpointed_render_and_p6(rtb, gpu_ctx, tmp_path):
     assert open(two).read() == open(one).read()
     r = run(two, {"RT_B200_CHECKPOINT": ck})  # a finished checkpoint: nothing left to render, same image
     assert r.returncode == 0 and open(two).read() == open(one).read()
+
+
+def test_very_bright_emitter_saturates_instead_of_wrapping(rtb, gpu_ctx):
+    """to_fixed clamps one sample at 2^16 before the 2^32 fixed-point scale (rt_b200.cu): an emitter of 1e5 seen directly
+    at 512 spp sums to 512 * 2^48 = 2^57 — inside the signed 64-bit range — instead of wrapping into garbage or negative
+    pixels (with the old 1e6 clamp 2,100 such samples overflowed).  write_color clips the mean at 0.999 either way: 255."""
+    import scene_util as su
+
+    s = su.SceneDesc()
+    sun = s.sphere((0, 0, 0), 1.0, s.light(s.solid(1e5, 2e5, 5e4)))
+    desc = s.finish(s.list([sun]))
+    cam = su.camera(width=48, spp=512, depth=4, bg=(0, 0, 0), lookfrom=(0, 0, 6), vfov=30.0)
+    gpu_ctx.upload_scene(desc)
+    gpu_ctx.render(cam, seed=1)
+    acc = gpu_ctx.download_accum()
+    assert (acc >= 0).all()
+    centre = acc[24, 24]
+    assert np.array_equal(centre, np.array([512 * 65536 << 32] * 2 + [512 * 50000 << 32]))  # r, g at the clamp; b = 5e4 exactly
+    assert np.array_equal(gpu_ctx.download_rgb8(512)[24, 24], [255, 255, 255])
+    assert not acc[0, 0].any()  # the black background
