@@ -93,6 +93,7 @@ struct DeviceScene {
   const int2* xchains;  // {first op, n ops}
   int n_nodes, n_spheres, n_quads, n_media, n_materials, n_textures, n_boxes, n_leaf_refs;
   int n_global_media;   // media that enclose the whole scene: sampled once per ray, not via the BVH
+  int n_noise;          // noise_texture tables (perlin_vec / perlin_perm): 0 = the scene has no Perlin texture
   int global_media[4];
   float scene_abs_max;  // max |coordinate| of any finite bound (conservative-cull epsilon scale)
   float bounds_lo[3], bounds_hi[3];  // union of every BVH item's box (= what node 0 covers); empty scene: +inf / -inf

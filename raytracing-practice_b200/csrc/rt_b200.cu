@@ -120,7 +120,9 @@ __global__ void push_kernel(const unsigned long long* __restrict__ accum, unsign
 // jitter-free pixel-centre ray of every pixel (no defocus, time 0, media transparent) and, instead of shading, writes
 // the primitive id, t and normal it found, so that the traversal rt_render runs is itself under the id / t / normal gate
 // (camera.hpp:192, hittable_list.hpp:40-64).
-template <bool COUNT, bool ALL_SMEM, bool SSTACK = false, bool AOV = false>
+// COOP = true evaluates Perlin turbulence warp-cooperatively (below); chosen per scene by the launch plan — only where a
+// good share of the primitives carries a noise texture: the hoisted hit record it needs costs the other scenes 3 %.
+template <bool COUNT, bool ALL_SMEM, bool SSTACK = false, bool AOV = false, bool COOP = false>
 __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_constant__ RenderParams P) {
   extern __shared__ float4 s_nodes[];
   stage_nodes<ALL_SMEM>(s_nodes, P.sc.nodes, P.smem_nodes);
@@ -275,6 +277,22 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
       }
       continue;
     }
+    // COOP: world.hit's record for the lanes that hit something (hit_record, face normal, uv: surface_at) is built BEFORE
+    // the shade, where the warp is still converged, and the lanes whose hit lands on a noise texture get their Perlin
+    // turbulence evaluated by the whole warp (rt_device.cuh, coop_noise_turb: seven lanes per requester, one octave each)
+    // instead of one lane after the other inside the divergent shade below.  Same bits as the serial loop.
+    Surface sf;
+    float turb_pre = -1.0f;  // a turbulence is |.| >= 0: negative = not evaluated here
+    if constexpr (COOP) {
+      const bool hit_something = alive && h.ref != REF_NONE;
+      if (hit_something) {
+        float tm, sk;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tm), "=f"(sk) : "r"(st_a + kStB + 8u));
+        sf = surface_at(sc, h, o, d, tm);
+      }
+      const int want = hit_something ? noise_request(sc, sf.material, sf.p) : -1;
+      turb_pre = coop_noise_turb(sc, want, hit_something ? sf.p : f3(0.0f, 0.0f, 0.0f), threadIdx.x & 31u);
+    }
     if (alive) {
       const float4 A = lds_f4(st_a), B = lds_f4(st_a + kStB);
       float3 beta = f3(A.x, A.y, A.z);
@@ -292,9 +310,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1) render_kernel(const __grid_
         alive = false;
       } else {
         const uint4 rnd = rng_block(key, bounce, 0u);
-        Surface sf = surface_at(sc, h, o, d, time);
+        if constexpr (!COOP) sf = surface_at(sc, h, o, d, time);
         float3 emit, atten, d_out;
-        bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn);
+        bool cont = scatter_ray<COUNT>(sc, sf, d, rnd, emit, atten, d_out, cn, turb_pre);
         L = L + beta * emit;
         if (cont) {
           beta = beta * atten;
@@ -569,6 +587,7 @@ struct rt_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  float noise_share = 0.0f;  // share of the BVH's primitives whose material can end in a noise texture (rt_upload_scene)
   // Process-environment knobs (experiments and test hooks, none needed for normal use), read ONCE when the context is
   // created: rt_render itself never looks at the environment, its behaviour is a function of its arguments and the context.
   //   RT_B200_KERNEL=mega|stream|refill  default render kernel        RT_B200_NO_STAGING=1   BVH top levels only in shared memory
@@ -932,6 +951,27 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
   s.scene_abs_max = h.scene_abs_max;
   for (int a = 0; a < 3; a++) s.bounds_lo[a] = h.bounds_lo[a], s.bounds_hi[a] = h.bounds_hi[a];
   s.n_global_media = int(h.global_media.size());
+  s.n_noise = int(h.perlin_vec.size() / 256);
+  {  // how much of the scene is marble?  (decides the render kernel instantiation, plan_megakernel)
+    auto may_noise = [&](int material) {
+      if (material < 0 || size_t(2 * material + 1) >= h.materials.size()) return false;
+      std::vector<int> todo{__builtin_bit_cast(int, h.materials[size_t(2 * material + 1)].y)};
+      for (int guard = 0; guard < 64 && !todo.empty(); guard++) {
+        const int tex = todo.back();
+        todo.pop_back();
+        if (tex < 0 || size_t(2 * tex + 1) >= h.textures.size()) continue;
+        const float4 t1 = h.textures[size_t(2 * tex + 1)];
+        const int kind = __builtin_bit_cast(int, t1.x);
+        if (kind == TEX_NOISE) return true;
+        if (kind == TEX_CHECKER) todo.push_back(__builtin_bit_cast(int, t1.y)), todo.push_back(__builtin_bit_cast(int, t1.z));
+      }
+      return false;
+    };
+    size_t prims = 0, marble = 0;
+    for (size_t i = 0; i < h.sph_meta.size(); i++) prims++, marble += may_noise(h.sph_meta[i].x);
+    for (size_t i = 0; i < h.quad_mat.size(); i++) prims++, marble += may_noise(h.quad_mat[i]);
+    ctx->noise_share = s.n_noise > 0 && prims > 0 ? float(marble) / float(prims) : 0.0f;
+  }
   for (int i = 0; i < 4; i++) s.global_media[i] = i < s.n_global_media ? h.global_media[size_t(i)] : -1;
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 #if RT_CHECKS
@@ -960,6 +1000,7 @@ int rt_upload_scene(rt_ctx* ctx, const rt_scene_desc* scene) {
 struct MegaPlan {
   size_t smem;
   bool all_smem, sstack;
+  bool coop_noise;  // the scene is largely noise-textured: the render kernel instantiation with cooperative turbulence
 };
 static MegaPlan plan_megakernel(const rt_ctx* ctx, RenderParams& P) {
   // the kernel is specialised for "the whole BVH — nodes, leaf references, spheres, boxes — is staged in shared
@@ -987,6 +1028,7 @@ static MegaPlan plan_megakernel(const rt_ctx* ctx, RenderParams& P) {
               smem + stack_bytes <= kSmemStackBudget && smem + stack_bytes + 4096 <= ctx->smem_optin;
   if (mp.sstack) P.stack_off = unsigned(smem), P.stack_levels = unsigned(std::max(1, ctx->host.bvh_depth)), smem += stack_bytes;
   mp.smem = smem;
+  mp.coop_noise = RT_COOP_NOISE && ctx->noise_share >= 0.125f;
   return mp;
 }
 
@@ -1206,6 +1248,8 @@ static int render_range(rt_ctx* ctx, const rt_camera_desc* cam, const rt_render_
     void (*kern)(RenderParams) = mp.sstack ? (count ? render_kernel<true, true, true> : render_kernel<false, true, true>)
                                            : count ? (mp.all_smem ? render_kernel<true, true> : render_kernel<true, false>)
                                                    : (mp.all_smem ? render_kernel<false, true> : render_kernel<false, false>);
+    if (mp.coop_noise && !count)  // scenes made of marble (perlin_sphere, simple_light): +8..13 %, gpurun_out/ab_coop.log
+      kern = mp.sstack ? render_kernel<false, true, true, false, true> : (mp.all_smem ? render_kernel<false, true, false, false, true> : render_kernel<false, false, false, false, true>);
     RT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // counters[0] = next work item: lanes take items with atomicAdd when they need one
     unsigned long long first = 0ull;

@@ -1022,6 +1022,59 @@ __device__ RT_OUTLINE float perlin_turb(const float4* __restrict__ vec, const ui
   return fabsf(accum);
 }
 
+#ifndef RT_COOP_NOISE
+#define RT_COOP_NOISE 1
+#endif
+// Will the texture of `material` end in a noise texture at point p?  Returns its table index, or -1.  (The walk of
+// texture_value down a checker nesting, without evaluating anything.)
+__device__ __forceinline__ int noise_request(const DeviceScene& sc, int material, float3 p) {
+  int tex = __float_as_int(__ldg(sc.materials + 2 * material + 1).y);
+#pragma unroll 1
+  for (int guard = 0; guard < 16 && tex >= 0; guard++) {
+    const float4 t0 = __ldg(sc.textures + 2 * tex), t1 = __ldg(sc.textures + 2 * tex + 1);
+    const int kind = __float_as_int(t1.x);
+    if (kind == TEX_NOISE) return __float_as_int(t1.y);
+    if (kind != TEX_CHECKER) return -1;
+    const int s = int(floorf(t0.w * p.x)) + int(floorf(t0.w * p.y)) + int(floorf(t0.w * p.z));
+    tex = (s & 1) ? __float_as_int(t1.z) : __float_as_int(t1.y);
+  }
+  return -1;
+}
+// noise.turb(p, 7) (texture.hpp:150, perlin.hpp) for the lanes with want >= 0, computed by the WHOLE converged warp: up to
+// four requesting lanes at a time get eight lanes each, lane k of a group evaluates octave k — perlin_noise(2^k p), the very
+// call the serial loop of perlin_turb makes in its k-th iteration (doubling is exact, so 2^k p has the bits of k doublings)
+// — and every requester then folds its seven octaves with the serial loop's own fmaf chain: bit-identical to perlin_turb,
+// whichever lanes ask together, so the image stays independent of the schedule.  More than four requesters (a scene made of
+// marble): every lane evaluates its own point, as before.  Returns the turbulence for requesters, -1 for the others.
+__device__ __forceinline__ float coop_noise_turb(const DeviceScene& sc, int want, float3 p, unsigned lane) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const unsigned m = __ballot_sync(FULL, want >= 0);
+  if (m == 0u) return -1.0f;
+  if (__popc(m) > 4) return want >= 0 ? perlin_turb(sc.perlin_vec + 256 * want, sc.perlin_perm + 768 * want, p) : -1.0f;
+  const unsigned grp = lane >> 3, k = lane & 7u;
+  unsigned mm = m;  // the grp-th requester = the grp-th set bit of m
+#pragma unroll
+  for (unsigned i = 0; i < 3; i++)
+    if (i < grp) mm &= mm - 1u;
+  const int src = mm ? __ffs(int(mm)) - 1 : 0;
+  const float px = __shfl_sync(FULL, p.x, src), py = __shfl_sync(FULL, p.y, src), pz = __shfl_sync(FULL, p.z, src);
+  const int idx = __shfl_sync(FULL, want, src);
+  float n = 0.0f;
+  if (mm != 0u && k < 7u) {
+    const float f = float(1u << k);
+    n = perlin_noise(sc.perlin_vec + 256 * idx, sc.perlin_perm + 768 * idx, f3(f * px, f * py, f * pz));
+  }
+  const unsigned rank = __popc(m & ((1u << lane) - 1u));  // a requester's group = its rank among the requesters
+  float accum = 0.0f, weight = 1.0f;
+#pragma unroll
+  for (int kk = 0; kk < 7; kk++) {
+    const float nk = __shfl_sync(FULL, n, int(((rank & 3u) << 3) + unsigned(kk)));
+    accum = fmaf(weight, nk, accum);
+    weight *= 0.5f;
+  }
+  return want >= 0 ? fabsf(accum) : -1.0f;
+}
+
 // get_sphere_uv (sphere.hpp:100-111) from the OBJECT-space outward normal
 __device__ __forceinline__ float2 sphere_uv(float3 n) {
   const float PI = 3.14159265358979323846f;
@@ -1031,7 +1084,7 @@ __device__ __forceinline__ float2 sphere_uv(float3 n) {
 }
 
 template <bool COUNT>
-__device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p, unsigned int* cn) {
+__device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, float u, float v, float3 p, unsigned int* cn, float turb_pre = -1.0f) {
 #pragma unroll 1
   for (int guard = 0; guard < 16; guard++) {
     RT_CHECK(tex >= 0 && tex < sc.n_textures, CHK_TEXTURE);
@@ -1059,7 +1112,8 @@ __device__ __forceinline__ float3 texture_value(const DeviceScene& sc, int tex, 
     }
     // TEX_NOISE: marble, texture.hpp:150
     if (COUNT) cn[CN_TEX_NOISE]++;
-    float turb = perlin_turb(sc.perlin_vec + 256 * a, sc.perlin_perm + 768 * a, p);
+    // (turb_pre >= 0: this lane's turbulence was already evaluated by coop_noise_turb — same point, same bits)
+    float turb = turb_pre >= 0.0f ? turb_pre : perlin_turb(sc.perlin_vec + 256 * a, sc.perlin_perm + 768 * a, p);
     float g = 0.5f * (1.0f + sinf(fmaf(t0.w, p.z, 10.0f * turb)));
     return f3(g, g, g);
   }
@@ -1195,7 +1249,7 @@ __device__ __forceinline__ Surface surface_at(const DeviceScene& sc, Hit h, floa
 // returns true when the path continues along (o, d); `emit` is material::emitted.
 template <bool COUNT>
 __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface& s, float3 d_in, uint4 rnd, float3& emit, float3& atten, float3& d_out,
-                                            unsigned int* cn) {
+                                            unsigned int* cn, float turb_pre = -1.0f) {
   RT_CHECK(s.material >= 0 && s.material < sc.n_materials, CHK_MATERIAL);
   float4 m0 = __ldg(sc.materials + 2 * s.material), m1 = __ldg(sc.materials + 2 * s.material + 1);
   const int kind = __float_as_int(m1.x), tex = __float_as_int(m1.y);
@@ -1203,7 +1257,7 @@ __device__ __forceinline__ bool scatter_ray(const DeviceScene& sc, const Surface
   if (COUNT) cn[CN_LAMB + (kind - MAT_LAMBERTIAN)]++;
   // one texture call site and one unit-vector site for all materials (code size: see RT_OUTLINE)
   float3 tv = f3(1.0f, 1.0f, 1.0f);
-  if (tex >= 0) tv = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn);
+  if (tex >= 0) tv = texture_value<COUNT>(sc, tex, s.u, s.v, s.p, cn, turb_pre);
   const float3 rv = unit_vector_from(u01(rnd.x), u01(rnd.y));
   switch (kind) {
     case MAT_LAMBERTIAN: {  // material.hpp:51-71
