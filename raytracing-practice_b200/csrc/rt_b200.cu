@@ -1028,6 +1028,9 @@ static MegaPlan plan_megakernel(const rt_ctx* ctx, RenderParams& P) {
               smem + stack_bytes <= kSmemStackBudget && smem + stack_bytes + 4096 <= ctx->smem_optin;
   if (mp.sstack) P.stack_off = unsigned(smem), P.stack_levels = unsigned(std::max(1, ctx->host.bvh_depth)), smem += stack_bytes;
   mp.smem = smem;
+  // (a "lazy" form for scenes with a LITTLE marble — only lanes whose hit material is flagged build a hit record ahead of the
+  //  shade — was measured on book2_final: bit-identical, -7 %; anything added to that scene's main loop costs more than the
+  //  6 % its one marble sphere does: gpurun_out/ab_lazy.log)
   mp.coop_noise = RT_COOP_NOISE && ctx->noise_share >= 0.125f;
   return mp;
 }
