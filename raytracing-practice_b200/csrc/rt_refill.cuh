@@ -7,8 +7,15 @@
 // have their answer: those lanes shade, regenerate and seed their next ray while the unfinished traversals stay
 // suspended (node index and stack pointer in two registers, the stack in local memory where it already was), and then
 // everybody traverses again.  Inside the traversal the warp takes a node step while at least RT_REFILL_NODE_THR lanes
-// want one and a leaf step otherwise.  tools/simt_sim (policy `inplace`) predicts 16-18 lanes in node_step and 1.3x
+// want one and a leaf step otherwise.  tools/simt_sim (policy `inplace`) predicted 16-18 lanes in node_step and 1.3x
 // fewer warp instructions per ray on book2_final for thresholds 16..24 / 8.
+//
+// MEASURED (profiles/r2_session_experiments.md, gpurun_out/refill_ab1.log, prof_rf1): bit-identical to the megakernel,
+// node_step at 13.9 lanes (6.8 there), traversal instructions -28 % — and 0.83x the megakernel's speed (0.85x with node
+// threshold 1, 0.90x with shade threshold 32 = the megakernel's own schedule in this loop shape): the shade round costs
+// about the same whether 20 or 31 lanes take it and now runs 1.45x as often (+70 % shade instructions), leaf phases — the
+// expensive kind of traversal step — multiply, and issue utilisation falls from 75 % to 62 %.  Kept as an opt-in,
+// tested experiment (RT_RENDER_REFILL); the production kernel is render_kernel.
 //
 // The register rule of the megakernel (anything live across the traversal or across the shade is paid for in occupancy)
 // is kept by PARKING: a ray's origin, direction and closest hit so far live in two more float4 records per thread in
