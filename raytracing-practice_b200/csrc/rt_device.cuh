@@ -379,6 +379,15 @@ __device__ __forceinline__ bool medium_span(const DeviceScene& sc, const DMedium
       t2 = r1 > t1 + 0.0001f ? r1 : INF;      // pass 2: the next crossing beyond t1 + 0.0001 (r0 itself never is)
       return t2 != INF;
     }
+    if ((ref >> 30) == REF_BOX) {  // a single box() (the Cornell smoke volumes): likewise ONE pair of roots instead of two
+      const uint32_t b = (ref & 0x3FFFFFFFu) >> 3;  // slab evaluations — the general passes below would compute the same r0, r1 twice
+      float r0, r1;
+      t1 = INF;
+      if (!box_roots(__ldg(sc.boxes + 3 * b), __ldg(sc.boxes + 3 * b + 1), __ldg(sc.boxes + 3 * b + 2), o, d, r0, r1)) return false;
+      t1 = r0;                                // pass 1
+      t2 = r1 >= t1 + 0.0001f ? r1 : INF;     // pass 2 (quads: interval::contains); r0 >= r0 + 0.0001 never holds
+      return t2 != INF;
+    }
   }
   t1 = INF;
   // pass 1: boundary->hit(r, universe): the smallest crossing
