@@ -26,6 +26,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -1058,7 +1059,14 @@ class context_cache {
     if (missing.size() > 1) {
       std::vector<int> rc(R, RT_OK);
       std::vector<std::thread> workers;
-      for (size_t r : missing) workers.emplace_back([this, r, &devices, &rc] { rc[r] = rt_init(devices[r], &slots_[r].ctx); });
+      for (size_t r : missing) {
+        auto job = [this, r, &devices, &rc] { rc[r] = rt_init(devices[r], &slots_[r].ctx); };
+        try {
+          workers.emplace_back(job);
+        } catch (const std::system_error&) {  // a program linked without thread support (old glibc, no -pthread): serially
+          job();
+        }
+      }
       for (std::thread& w : workers) w.join();
       for (size_t r : missing) {
         if (rc[r] != RT_OK) die(nullptr, "rt_init", rc[r]);
@@ -1137,7 +1145,14 @@ inline void camera::render(std::ostream& output_stream, const hittable& world) {
   } else {  // the BVH build + upload of every device's copy, concurrently (rt_upload_scene is synchronous)
     std::vector<int> rcs(size_t(R), RT_OK);
     std::vector<std::thread> workers;
-    for (int r = 0; r < R; r++) workers.emplace_back([&, r] { rcs[size_t(r)] = rt_upload_scene(ctx[size_t(r)], &sd); });
+    for (int r = 0; r < R; r++) {
+      auto job = [&, r] { rcs[size_t(r)] = rt_upload_scene(ctx[size_t(r)], &sd); };
+      try {
+        workers.emplace_back(job);
+      } catch (const std::system_error&) {
+        job();
+      }
+    }
     for (std::thread& w : workers) w.join();
     for (int r = 0; r < R; r++)
       if (rcs[size_t(r)] != RT_OK) rtb200::die(ctx[size_t(r)], "rt_upload_scene", rcs[size_t(r)]);
