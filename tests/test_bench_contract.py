@@ -32,3 +32,26 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 
 def test_reference_arm_other_ranks_exit_quietly():
     assert run_arm({"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_ncu_figures_are_tied_to_the_kernel_code_not_to_its_comments(tmp_path, monkeypatch):
+    """bench.py quotes DRAM traffic / issue utilisation / active lanes only from an ncu capture of THESE kernels
+    (profiles/latest_ncu.json carries a hash of csrc/ with comments and whitespace removed): rewording a comment keeps the
+    figures, changing a token drops them."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, ROOT)
+    mod = importlib.import_module("raytracing-practice_b200.csrc_sha")
+    a = "int f(int x) { // add one\n  return x + 1; /* here */ }\n"
+    b = "int f(int x) {   // plus one, reworded\n\n  return x + 1; }\n"
+    c = "int f(int x) { return x + 2; }\n"
+    assert mod._code_only(a) == mod._code_only(b) != mod._code_only(c)
+    assert mod._code_only('const char* s = "// not a comment";') == 'const char* s = "// not a comment";'
+    import bench
+
+    ncu, src = bench.latest_ncu()
+    if ncu is not None:  # the committed capture matches the tree: its keys are the ones bench.py reads
+        assert ncu["csrc_sha"] == bench.csrc_sha() and ncu["dram_bytes_per_sample"] > 0 and 0 < ncu["issue_slot_utilisation"] <= 1
+    else:
+        assert "omitted" in src or "missing" in src
