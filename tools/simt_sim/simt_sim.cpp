@@ -9,7 +9,21 @@
 //   policy mega : render_kernel as shipped in round 1 (a lane owns a path; while-while traversal; shade in place)
 //   policy wq   : trace warps whose lanes take rays from a CTA-wide queue the moment enough of them are idle,
 //                 shade in dense batches of 32 finished rays
-// Build: make -C tools/simt_sim      Run: tools/simt_sim/simt_sim book2_final mega|wq [key=value ...]
+//   policy inplace : the megakernel with in-place lane refill (the warp leaves the traversal once `shade_thr` lanes wait)
+//   policy sym  : symmetric warps over CTA-wide queues
+// Build: make -C tools/simt_sim      Run: tools/simt_sim/simt_sim book2_final mega|wq|sym|inplace [key=value ...]
+//
+// REALITY CHECK (round 2, profiles/r2_session_experiments.md).  The model reproduces the megakernel well (8.16 node visits per
+// ray, 7.4 lanes in node_step against ncu's 6.8, 117 warp instructions per ray against 143) and its LANE predictions hold up
+// on the GPU (in-place refill: 16-18 lanes predicted in node_step, 13.9 measured).  Its TIME predictions do not: it gave the
+// refill schedule 1.30x, a node-step threshold 1.06x and the queue-fed kernel 1.45x fewer instructions; measured speeds are
+// 0.83x, 0.81-0.89x and 0.46x.  What it lacks: (1) a shade round is charged per material group that is present, but on the GPU
+// the long divergent shade costs ~1,350 warp instructions almost regardless of how many lanes take part, so every schedule
+// that shades more often pays in full; (2) a leaf phase is charged 10 + 30..55 per primitive, the real one (six-way type
+// dispatch at ~4 lanes, dependent shared-memory reads, the pop that follows) costs several times that, so schedules that
+// multiply leaf phases lose; (3) it counts issued instructions only — the kernel is bound by the ALU pipe and by latency at 28
+// warps per SM, and the reordered schedules drop issue utilisation from 75 % to 43-62 %.  Use it for lane statistics and ray
+// census, not for speed-ups.
 #include <cuda_runtime.h>  // the shim
 #include <cstdio>
 #include <cstdlib>
