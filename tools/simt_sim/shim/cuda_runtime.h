@@ -52,5 +52,13 @@ inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 inline bool __any_sync(unsigned, bool p) { return p; }
 inline bool __all_sync(unsigned, bool p) { return p; }
 inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+// one-lane "warp": enough for the device routines the simulator calls per lane (the warp-cooperative ones only have to compile)
+template <typename T> inline T __shfl_sync(unsigned, T v, int) { return v; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline float __fsub_ru(float a, float b) { return std::nextafter(a - b, INFINITY); }
+struct shim_dim3 { unsigned x = 0, y = 0, z = 0; };
+static shim_dim3 threadIdx, blockIdx;
+static shim_dim3 blockDim{1, 1, 1};
 using std::max;
 using std::min;
